@@ -1,0 +1,655 @@
+# -*- coding: utf-8 -*-
+"""
+Flow compiler and ``calculate_vars`` tracer.
+
+Lowers a ``BaseModel`` (popdynamics_b200/basepop.py; reference /root/reference/basepop.py) into
+
+* a flat SoA **flow table** of ``(kind, from, to, rate slot)`` rows in the canonical evaluation
+  order of ``calculate_flows`` / ``calculate_events`` (basepop.py:566-598, :703-735): entry flows,
+  var transfers, fixed transfers, one background-death row per compartment, infection deaths;
+* an fp64 **expression DAG** obtained by running the user's ``calculate_vars`` hook
+  (basepop.py:553) ONCE with symbolic proxies for ``self.compartments`` / ``self.params`` /
+  ``self.vars`` / ``self.time``.  Operations are recorded in program order and never
+  re-associated, so the device evaluates exactly the reference's arithmetic (kernels are built
+  with ``--fmad=false``).
+
+The DAG is emitted twice: as CUDA C for NVRTC (``cuda_source``) and as a tiny bytecode that the
+CPU oracle interprets (``oracle_program``; tests only).  Python constructs that cannot be lowered
+(``bool()`` of a traced value, ``math.*`` on it, ``int()``/``float()``, ``**``, numpy ufuncs) raise
+``TraceError`` -- nothing is silently run on the CPU.
+"""
+
+from __future__ import division
+
+import builtins
+import contextlib
+import hashlib
+import math
+import numbers
+
+import numpy
+
+ENTRY, VAR, FIXED, BGDEATH, INFDEATH = 0, 1, 2, 3, 4
+KIND_NAMES = ('entry', 'var', 'fixed', 'bgdeath', 'infdeath')
+
+# opcode numbering shared with oracle/popdyn_oracle.h
+OPS = ('const', 'add', 'sub', 'mul', 'div', 'neg', 'fabs', 'floor', 'lt', 'le', 'gt', 'ge',
+       'eq', 'ne', 'and', 'or', 'not', 'isfinite', 'select')
+OPCODE = {name: i for i, name in enumerate(OPS)}
+_BOOL_OPS = frozenset(('lt', 'le', 'gt', 'ge', 'eq', 'ne', 'and', 'or', 'not', 'isfinite'))
+
+
+class TraceError(TypeError):
+    """A Python construct in a traced hook cannot be lowered to the device."""
+
+
+# =============================================================================================
+# expression graph
+# =============================================================================================
+
+class Graph(object):
+    """Hash-consed expression DAG.  Node = (op, a, b, c); leaves are ('comp', i), ('param', j),
+    ('time',), ('su', k), ('const', repr)."""
+
+    def __init__(self):
+        self.nodes = []
+        self.index = {}
+        self.const_values = {}
+        self.assertions = []   # node ids recorded by traced `assert` statements
+        self.collect_asserts = False
+
+    def add(self, op, a=-1, b=-1, c=-1):
+        key = (op, a, b, c)
+        hit = self.index.get(key)
+        if hit is None:
+            hit = len(self.nodes)
+            self.nodes.append(key)
+            self.index[key] = hit
+        return hit
+
+    def const(self, value):
+        value = float(value)
+        key = ('const', value.hex())
+        hit = self.index.get(key)
+        if hit is None:
+            hit = len(self.nodes)
+            self.nodes.append(key)
+            self.index[key] = hit
+            self.const_values[hit] = value
+        return hit
+
+
+def _is_intlike(x):
+    return isinstance(x, numbers.Integral) and not isinstance(x, bool)
+
+
+class Sym(object):
+    """Symbolic fp64 value.  ``is_int`` records whether the Python value would be an ``int``
+    (stochastic integrators hold integer compartments, basepop.py:747-748, :805-806): it steers
+    ``old_div`` and the path Python's ``sum`` takes, the value itself is always carried in fp64
+    (exact below 2**53)."""
+
+    __slots__ = ('g', 'n', 'is_int', 'is_bool')
+    __array_ufunc__ = None      # numpy scalars defer to our reflected operators
+    __hash__ = None
+
+    def __init__(self, g, n, is_int=False, is_bool=False):
+        self.g, self.n, self.is_int, self.is_bool = g, n, is_int, is_bool
+
+    # -- coercion ---------------------------------------------------------------------------
+    def _lift(self, other):
+        if isinstance(other, Sym):
+            if other.g is not self.g:
+                raise TraceError('traced values from two different traces were mixed')
+            return other
+        if isinstance(other, bool):
+            return Sym(self.g, self.g.const(float(other)), is_int=True)
+        if isinstance(other, numbers.Real):
+            return Sym(self.g, self.g.const(float(other)), is_int=_is_intlike(other))
+        if isinstance(other, numpy.ndarray):
+            raise TraceError('numpy arrays cannot be mixed with traced values inside a hook; '
+                             'pass per-member arrays through set_param / set_compartment')
+        return None
+
+    def _bin(self, op, other, swap=False):
+        rhs = self._lift(other)
+        if rhs is None:
+            return NotImplemented
+        a, b = (rhs, self) if swap else (self, rhs)
+        if a.is_bool or b.is_bool:
+            raise TraceError('arithmetic on a traced comparison result is not supported')
+        as_int = a.is_int and b.is_int and op != 'div'
+        return Sym(self.g, self.g.add(op, a.n, b.n), is_int=as_int)
+
+    def __add__(self, o): return self._bin('add', o)
+    def __radd__(self, o): return self._bin('add', o, True)
+    def __sub__(self, o): return self._bin('sub', o)
+    def __rsub__(self, o): return self._bin('sub', o, True)
+    def __mul__(self, o): return self._bin('mul', o)
+    def __rmul__(self, o): return self._bin('mul', o, True)
+    def __truediv__(self, o): return self._bin('div', o)
+    def __rtruediv__(self, o): return self._bin('div', o, True)
+
+    def __floordiv__(self, o):
+        rhs = self._lift(o)
+        if rhs is None:
+            return NotImplemented
+        return _floordiv(self, rhs)
+
+    def __rfloordiv__(self, o):
+        lhs = self._lift(o)
+        if lhs is None:
+            return NotImplemented
+        return _floordiv(lhs, self)
+
+    def __neg__(self):
+        return Sym(self.g, self.g.add('neg', self.n), is_int=self.is_int)
+
+    def __pos__(self):
+        return self
+
+    def __abs__(self):
+        return Sym(self.g, self.g.add('fabs', self.n), is_int=self.is_int)
+
+    def _cmp(self, op, other):
+        rhs = self._lift(other)
+        if rhs is None:
+            return NotImplemented
+        return Sym(self.g, self.g.add(op, self.n, rhs.n), is_bool=True)
+
+    def __lt__(self, o): return self._cmp('lt', o)
+    def __le__(self, o): return self._cmp('le', o)
+    def __gt__(self, o): return self._cmp('gt', o)
+    def __ge__(self, o): return self._cmp('ge', o)
+    def __eq__(self, o): return self._cmp('eq', o)
+    def __ne__(self, o): return self._cmp('ne', o)
+
+    # -- loud rejections --------------------------------------------------------------------
+    def __bool__(self):
+        if self.g.collect_asserts:
+            # inside a traced checks(): `assert cond` becomes a device-side assertion
+            self.g.assertions.append(self.n)
+            return True
+        raise TraceError(
+            'a traced value was used in a Python branch (if / while / and / or / min / max); '
+            'data-dependent control flow in calculate_vars cannot be lowered to the device')
+
+    def _no_scalar(self, *args):
+        raise TraceError(
+            'a traced value was converted with float() / int() / math.* ; only + - * / '
+            'abs() sum() old_div() and comparisons inside checks() are lowered to the device')
+
+    __float__ = __int__ = __index__ = __complex__ = __round__ = __trunc__ = _no_scalar
+    __floor__ = __ceil__ = _no_scalar
+
+    def __pow__(self, o, mod=None):
+        raise TraceError('** on a traced value is not lowered (libm pow has no bit-exact '
+                         'device counterpart); write the product out')
+
+    __rpow__ = __pow__
+
+    def __mod__(self, o):
+        raise TraceError('% on a traced value is not supported')
+
+    __rmod__ = __mod__
+
+    def __repr__(self):
+        return 'Sym(#%d%s)' % (self.n, ',int' if self.is_int else '')
+
+
+def _floordiv(a, b):
+    if not (a.is_int and b.is_int):
+        raise TraceError('// is only lowered for two integer operands')
+    q = a.g.add('div', a.n, b.n)
+    return Sym(a.g, a.g.add('floor', q), is_int=True)
+
+
+def sym_old_div(a, b):
+    """``past.utils.old_div`` on traced values: floor division for two ints, else true division."""
+    sym = a if isinstance(a, Sym) else b
+    a, b = sym._lift(a), sym._lift(b)
+    if a is None or b is None:
+        raise TraceError('old_div operand cannot be traced')
+    if a.is_int and b.is_int:
+        return _floordiv(a, b)
+    return a / b
+
+
+def traced_sum(iterable, start=0, naive=False):
+    """Python's builtin ``sum`` over traced floats.
+
+    CPython >= 3.12 (Python/bltinmodule.c, builtin_sum_impl) sums exact ``float`` objects with
+    Neumaier compensation: leading ints are accumulated exactly, the first float is added
+    plainly, later floats update ``(f, c)`` and ``c`` is added at the end when finite and
+    non-zero.  ``naive=True`` emits the plain left fold instead (what ``sum`` does over
+    ``numpy.float64`` items, i.e. after ``integrate(is_continue=True)``, and on CPython < 3.12).
+    """
+    items = list(iterable)
+    if not any(isinstance(x, Sym) for x in items) and not isinstance(start, Sym):
+        return _real_sum(items, start)
+    total = start
+    k = 0
+    # exact part: while everything seen is an int (or nothing symbolic yet)
+    while k < len(items) and (_is_intlike(items[k]) or
+                              (isinstance(items[k], Sym) and items[k].is_int)):
+        total = _fold0(total, items[k])
+        k += 1
+    if k == len(items):
+        return total
+    total = _fold0(total, items[k])            # first float: plain add
+    k += 1
+    if naive:
+        for x in items[k:]:
+            total = total + x
+        return total
+    g = total.g if isinstance(total, Sym) else next(x for x in items if isinstance(x, Sym)).g
+    if not isinstance(total, Sym):
+        total = Sym(g, g.const(total))
+    comp = None
+    for x in items[k:]:
+        if _is_intlike(x) or (isinstance(x, Sym) and x.is_int):
+            total = total + x                    # ints on the float path: plain add
+            continue
+        x = total._lift(x)
+        t = total + x
+        bigger = Sym(g, g.add('ge', g.add('fabs', total.n), g.add('fabs', x.n)), is_bool=True)
+        lo1 = (total - t) + x
+        lo2 = (x - t) + total
+        term = Sym(g, g.add('select', bigger.n, lo1.n, lo2.n))
+        comp = term if comp is None else comp + term
+        total = t
+    if comp is not None:
+        nonzero = g.add('ne', comp.n, g.const(0.0))
+        finite = g.add('isfinite', comp.n)
+        cond = g.add('and', nonzero, finite)
+        total = Sym(g, g.add('select', cond, (total + comp).n, total.n))
+    return total
+
+
+def _fold0(total, x):
+    """``total + x`` where an exact int 0 on the left is dropped (``0 + x``)."""
+    if _is_intlike(total) and total == 0 and isinstance(x, Sym):
+        return x
+    return total + x
+
+
+_real_sum = builtins.sum
+
+
+@contextlib.contextmanager
+def _patched_sum(naive):
+    def hooked(iterable, start=0):
+        return traced_sum(iterable, start, naive=naive)
+    builtins.sum = hooked
+    try:
+        yield
+    finally:
+        builtins.sum = _real_sum
+
+
+# =============================================================================================
+# traced views of the model's dictionaries
+# =============================================================================================
+
+class _ParamView(dict):
+    """``self.params`` during a trace: numeric values come back as parameter symbols."""
+
+    def __init__(self, tracer, source):
+        dict.__init__(self, source)
+        self._tracer = tracer
+
+    def __getitem__(self, label):
+        value = dict.__getitem__(self, label)
+        sym = self._tracer.param_symbol(label, value)
+        return value if sym is None else sym
+
+    def get(self, label, default=None):
+        return self[label] if label in self else default
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+
+class CompiledModel(object):
+    """Result of ``compile_model``: flow table, expression DAG, parameter / scale-up tables."""
+
+    def __init__(self):
+        self.labels = []
+        self.method = None
+        self.integer_state = False
+        self.naive_sum = False
+        self.graph = None
+        self.order = []            # node ids in evaluation order (after dead-code elimination)
+        self.param_labels = []     # slot -> label (None for anonymous constants)
+        self.param_values = []     # slot -> float or 1-D array (per member)
+        self.param_is_int = []
+        self.su_labels = []
+        self.flow_kind = []
+        self.flow_from = []
+        self.flow_to = []
+        self.flow_node = []        # DAG node holding the rate multiplier
+        self.flow_is_int = []
+        self.flow_names = []
+        self.check_nodes = []
+        self.uses_time = False
+        self.var_nodes = {}        # var label -> node id (all vars seen in the trace)
+
+    # ---- sizes
+    @property
+    def n_comp(self): return len(self.labels)
+    @property
+    def n_flow(self): return len(self.flow_kind)
+    @property
+    def n_param(self): return len(self.param_labels)
+    @property
+    def n_su(self): return len(self.su_labels)
+
+    def member_param_slots(self):
+        return [k for k, v in enumerate(self.param_values) if isinstance(v, numpy.ndarray)]
+
+    def n_members_implied(self):
+        sizes = set(v.size for v in self.param_values if isinstance(v, numpy.ndarray))
+        if len(sizes) > 1:
+            raise ValueError('per-member parameter arrays have different lengths: %s' % sizes)
+        return sizes.pop() if sizes else None
+
+    def uniform_params(self):
+        """fp64 vector of all parameter slots; per-member slots hold NaN as a tripwire."""
+        return numpy.array([numpy.nan if isinstance(v, numpy.ndarray) else float(v)
+                            for v in self.param_values], dtype=numpy.float64)
+
+    def flow_table(self):
+        """The flat SoA flow table: int32 arrays kind / from / to (-1 = outside)."""
+        as_i32 = lambda seq: numpy.asarray(seq, dtype=numpy.int32)
+        return dict(kind=as_i32(self.flow_kind), frm=as_i32(self.flow_from),
+                    to=as_i32(self.flow_to), is_int=as_i32(self.flow_is_int))
+
+    # ---- oracle bytecode (tests only consume it; building it is plain host logic) ----------
+    def oracle_program(self):
+        g = self.graph
+        C, NP, NSU = self.n_comp, self.n_param, self.n_su
+        base = C + NP + 1 + NSU
+        slot_of, ins, consts = {}, [], []
+        for n in self.order:
+            node = g.nodes[n]
+            op = node[0]
+            if op == 'comp':
+                slot_of[n] = node[1]
+            elif op == 'param':
+                slot_of[n] = C + node[1]
+            elif op == 'time':
+                slot_of[n] = C + NP
+            elif op == 'su':
+                slot_of[n] = C + NP + 1 + node[1]
+            elif op == 'const':
+                consts.append(g.const_values[n])
+                slot_of[n] = base + len(ins)
+                ins.append((OPCODE['const'], len(consts) - 1, -1, -1))
+            else:
+                args = [slot_of[x] if x >= 0 else -1 for x in node[1:]]
+                slot_of[n] = base + len(ins)
+                ins.append((OPCODE[op], args[0], args[1], args[2]))
+        return dict(
+            ins=numpy.asarray(ins, dtype=numpy.int32).reshape(-1, 4),
+            consts=numpy.asarray(consts, dtype=numpy.float64),
+            slot=numpy.asarray([slot_of[n] for n in self.flow_node], dtype=numpy.int32),
+            check=numpy.asarray([slot_of[n] for n in self.check_nodes], dtype=numpy.int32),
+            n_values=base + len(ins), slot_of=slot_of)
+
+    # ---- CUDA C for NVRTC ------------------------------------------------------------------
+    def cuda_source(self):
+        from .codegen import emit_model_header
+        return emit_model_header(self)
+
+    def structure_key(self):
+        """Hash of everything that shapes the generated kernel (NOT parameter values)."""
+        h = hashlib.sha256()
+        h.update(self.cuda_source().encode())
+        return h.hexdigest()[:24]
+
+
+class _Tracer(object):
+    def __init__(self, model, integer_state):
+        self.model = model
+        self.g = Graph()
+        self.integer_state = integer_state
+        self.param_slot = {}
+        self.param_labels, self.param_values, self.param_is_int = [], [], []
+
+    def param_symbol(self, label, value):
+        if isinstance(value, Sym):
+            return value
+        if isinstance(value, bool) or not (isinstance(value, numbers.Real) or
+                                           isinstance(value, numpy.ndarray)):
+            return None                       # strings, lists ...: static Python data
+        slot = self.param_slot.get(label)
+        if slot is None:
+            slot = len(self.param_labels)
+            self.param_slot[label] = slot
+            self.param_labels.append(label)
+            if isinstance(value, numpy.ndarray):
+                if value.ndim != 1:
+                    raise ValueError('parameter %r: only 1-D per-member arrays are supported'
+                                     % (label,))
+                value = numpy.ascontiguousarray(value, dtype=numpy.float64)
+            self.param_values.append(value)
+            self.param_is_int.append(_is_intlike(value))
+        return Sym(self.g, self.g.add('param', slot), is_int=self.param_is_int[slot])
+
+    def anonymous_param(self, value, tag):
+        return self.param_symbol('<%s>' % tag, value)
+
+
+def compile_model(model, method, is_continue=False, naive_sum=None):
+    """Lower ``model`` for ``method`` ('explicit', 'discrete_time_stochastic',
+    'continuous_time_stochastic').  ``model.set_flows()`` must already have run
+    (``check_flow_transfers``, basepop.py:638-656)."""
+    from .basepop import BaseModel
+
+    integer_state = method != 'explicit'
+    if naive_sum is None:
+        # after is_continue the compartments are numpy.float64 (basepop.py:932-933) and Python's
+        # sum() falls off its compensated float fast path
+        naive_sum = bool(is_continue) and not integer_state
+    tr = _Tracer(model, integer_state)
+    g = tr.g
+    cm = CompiledModel()
+    cm.labels = list(model.labels)
+    cm.method = method
+    cm.integer_state = integer_state
+    cm.naive_sum = naive_sum
+    cm.graph = g
+    index_of = {label: i for i, label in enumerate(cm.labels)}
+
+    comps = {label: Sym(g, g.add('comp', i), is_int=integer_state)
+             for i, label in enumerate(cm.labels)}
+    time_sym = Sym(g, g.add('time'))
+
+    # ---- vars dictionary at the start of the hook -----------------------------------------
+    if method == 'explicit':
+        # prepare_vars_and_flows: vars.clear(); scale-ups; calculate_vars (basepop.py:606-610)
+        cm.su_labels = list(model.scaleup_fns.keys())
+        traced_vars = {label: Sym(g, g.add('su', k)) for k, label in enumerate(cm.su_labels)}
+    else:
+        # the stochastic loops never clear vars nor evaluate scale-ups (basepop.py:763-765,
+        # :822-824): whatever is left in self.vars is visible as stale constants
+        traced_vars = {k: v for k, v in model.vars.items() if isinstance(v, numbers.Real)}
+
+    # flow lists whose resolved rates are parameter symbols while the hooks run
+    fixed_syms = []
+    for from_label, to_label, rate in model.fixed_transfer_rate_flows:
+        plabel = model._fixed_rate_params.get((from_label, to_label))
+        if plabel is not None and plabel in model.params and _same(model.params[plabel], rate):
+            sym = tr.param_symbol(plabel, model.params[plabel])
+        else:
+            sym = tr.anonymous_param(rate, 'fixed:%s>%s' % (from_label, to_label))
+        fixed_syms.append((from_label, to_label, sym))
+    inf_syms = []
+    for label, rate in model.infection_death_rate_flows:
+        plabel = model._infection_death_params.get(label)
+        if plabel is not None and plabel in model.params and _same(model.params[plabel], rate):
+            sym = tr.param_symbol(plabel, model.params[plabel])
+        else:
+            sym = tr.anonymous_param(rate, 'infdeath:%s' % label)
+        inf_syms.append((label, sym))
+    bg = model.background_death_rate
+    plabel = model._background_death_param
+    bg_is_default = plabel is None and not isinstance(bg, numpy.ndarray) and bg == 0.
+    if bg_is_default:
+        bg_sym = None
+    elif plabel is not None and plabel in model.params and _same(model.params[plabel], bg):
+        bg_sym = tr.param_symbol(plabel, model.params[plabel])
+    else:
+        bg_sym = tr.anonymous_param(bg, 'background_death')
+
+    saved = dict(params=model.params, compartments=model.compartments, vars=model.vars,
+                 time=model.time, fixed=model.fixed_transfer_rate_flows,
+                 inf=model.infection_death_rate_flows, bg=model.background_death_rate)
+    try:
+        model.params = _ParamView(tr, saved['params'])
+        model.compartments = comps
+        model.vars = traced_vars
+        model.time = time_sym
+        model.fixed_transfer_rate_flows = fixed_syms
+        model.infection_death_rate_flows = inf_syms
+        if bg_sym is not None:
+            model.background_death_rate = bg_sym
+        with _patched_sum(naive_sum):
+            model.calculate_vars()
+        hook_vars = dict(model.vars)
+
+        def as_sym(value, what):
+            if isinstance(value, Sym):
+                if value.is_bool:
+                    raise TraceError('%s is a comparison result, not a number' % what)
+                return value
+            if isinstance(value, numbers.Real):
+                return Sym(g, g.const(float(value)), is_int=_is_intlike(value))
+            raise TraceError('%s has unsupported type %s' % (what, type(value).__name__))
+
+        # ---- flow table in canonical order (basepop.py:566-598 / :703-735) -----------------
+        def add_flow(kind, frm, to, sym, name):
+            cm.flow_kind.append(kind)
+            cm.flow_from.append(-1 if frm is None else index_of[frm])
+            cm.flow_to.append(-1 if to is None else index_of[to])
+            cm.flow_node.append(sym.n)
+            cm.flow_is_int.append(1 if (kind == ENTRY and sym.is_int) else 0)
+            cm.flow_names.append(name)
+
+        for label, var_label in model.var_entry_rate_flow:
+            add_flow(ENTRY, None, label, as_sym(hook_vars[var_label], 'vars[%r]' % var_label),
+                     '->%s [%s]' % (label, var_label))
+        for from_label, to_label, var_label in model.var_transfer_rate_flows:
+            add_flow(VAR, from_label, to_label,
+                     as_sym(hook_vars[var_label], 'vars[%r]' % var_label),
+                     '%s->%s [%s]' % (from_label, to_label, var_label))
+        for from_label, to_label, sym in fixed_syms:
+            add_flow(FIXED, from_label, to_label, sym, '%s->%s' % (from_label, to_label))
+        if bg_sym is not None:
+            for label in cm.labels:
+                add_flow(BGDEATH, label, None, bg_sym, '%s->death' % label)
+        for label, sym in inf_syms:
+            add_flow(INFDEATH, label, None, sym, '%s->infection death' % label)
+
+        # ---- checks() ----------------------------------------------------------------------
+        default_checks = type(model).checks is BaseModel.checks
+        if default_checks:
+            zero = g.const(0.0)
+            cm.check_nodes = [g.add('ge', comps[label].n, zero) for label in cm.labels]
+            if integer_state:
+                cm.check_nodes = []       # integer counts never go negative (clamped draws)
+        else:
+            if integer_state:
+                raise TraceError(
+                    'a user-defined checks() is only lowered for the explicit integrator; the '
+                    'stochastic integrators keep the default non-negativity invariant')
+            # vars visible to checks(): calculate_flows has also defined the two death totals
+            rate_death, rate_inf = _death_totals(cm, g, comps, bg_sym, inf_syms)
+            model.vars['rate_death'] = rate_death
+            model.vars['rate_infection_death'] = rate_inf
+            g.collect_asserts = True
+            try:
+                with _patched_sum(naive_sum):
+                    model.checks()
+            finally:
+                g.collect_asserts = False
+            cm.check_nodes = list(g.assertions)
+        cm.var_nodes = {k: as_sym(v, 'vars[%r]' % k).n for k, v in hook_vars.items()
+                        if isinstance(v, (Sym, numbers.Real)) and not getattr(v, 'is_bool', False)}
+    finally:
+        model.params = saved['params']
+        model.compartments = saved['compartments']
+        model.vars = saved['vars']
+        model.time = saved['time']
+        model.fixed_transfer_rate_flows = saved['fixed']
+        model.infection_death_rate_flows = saved['inf']
+        model.background_death_rate = saved['bg']
+
+    cm.param_labels = tr.param_labels
+    cm.param_values = tr.param_values
+    cm.param_is_int = tr.param_is_int
+
+    # ---- dead-code elimination + evaluation order --------------------------------------------
+    roots = list(cm.flow_node) + list(cm.check_nodes)
+    live = set()
+    stack = list(roots)
+    while stack:
+        n = stack.pop()
+        if n in live:
+            continue
+        live.add(n)
+        node = g.nodes[n]
+        if node[0] not in ('comp', 'param', 'time', 'su', 'const'):
+            stack.extend(x for x in node[1:] if x >= 0)
+    cm.order = [n for n in range(len(g.nodes)) if n in live]   # creation order is topological
+    cm.uses_time = any(g.nodes[n][0] == 'time' for n in cm.order)
+    return cm
+
+
+def _same(a, b):
+    if isinstance(a, numpy.ndarray) or isinstance(b, numpy.ndarray):
+        return a is b
+    return a == b
+
+
+def _death_totals(cm, g, comps, bg_sym, inf_syms):
+    """vars['rate_death'] / vars['rate_infection_death'] as calculate_flows accumulates them
+    (basepop.py:587-598)."""
+    rate_death = 0.
+    if bg_sym is not None:
+        for label in cm.labels:
+            rate_death = rate_death + comps[label] * bg_sym
+    rate_inf = 0.
+    for label, sym in inf_syms:
+        rate_inf = rate_inf + comps[label] * sym
+    return rate_death, rate_inf
+
+
+def explicit_schedule(target_times, min_dt=0.05):
+    """Host replay of the sub-step schedule of ``integrate_explicit`` (basepop.py:672-682).  It is
+    member independent: fp64 accumulation ``time = time + min_dt`` with a snap to the target on
+    overshoot, so some intervals take 21 sub-steps, the last with dt ~ 1e-16.  Returns
+    ``(t_eval, dt, n_sub)``: evaluation time and step size of every derivative call, and the
+    number of sub-steps in each of the T-1 target intervals."""
+    t_eval, dts, n_sub = [], [], []
+    time = float(target_times[0])
+    min_dt = float(min_dt)
+    for new_time in target_times[1:]:
+        new_time = float(new_time)
+        count = 0
+        while time < new_time:
+            old_time = time
+            time = time + min_dt
+            dt = min_dt
+            if time > new_time:
+                dt = new_time - old_time
+                time = new_time
+            t_eval.append(old_time)
+            dts.append(dt)
+            count += 1
+        n_sub.append(count)
+    return (numpy.asarray(t_eval, dtype=numpy.float64), numpy.asarray(dts, dtype=numpy.float64),
+            numpy.asarray(n_sub, dtype=numpy.int32))
