@@ -1,0 +1,162 @@
+/*
+ * popdyn_b200.h -- C-ABI of libpopdyn_b200.so, the B200 engine behind popdynamics' BaseModel
+ * integrators.
+ *
+ * The reference (popdynamics/popdynamics) is pure Python and has no FFI layer: the drop-in
+ * boundary is the Python class API of basepop.BaseModel (reference basepop.py:184-558,
+ * integrate() at :854-903).  This C-ABI therefore sits UNDER that class: it is exactly what a
+ * ctypes binding inside the reference's `integrate` would call instead of its three Python loops.
+ * Each entry point cites the reference code it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every data pointer may be HOST memory (numpy) or
+ * DEVICE memory (torch / cudaMalloc) -- the library looks at the pointer's attributes, stages
+ * host buffers through the device inside the call and leaves device buffers in place.  All
+ * functions return 0 on success or a negative pd_status; pd_last_error() gives the message of
+ * the calling thread's last failure.  Handles are thread-compatible, not thread-safe.  There is
+ * no CPU fallback: without a CUDA device the run functions fail with PD_E_NO_DEVICE.
+ */
+#ifndef POPDYN_B200_H
+#define POPDYN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PD_OK = 0,
+  PD_E_INVALID = -1,   /* bad argument                                                        */
+  PD_E_COMPILE = -2,   /* NVRTC rejected the generated model (log in pd_last_error)           */
+  PD_E_CUDA = -3,      /* CUDA runtime / driver error                                         */
+  PD_E_NO_DEVICE = -4, /* no usable GPU                                                       */
+  PD_E_MODEL = -5      /* device-side error flag raised (see pd_run_result.err_*)             */
+} pd_status;
+
+/* integrator selector: which reference loop the compiled kernel replaces */
+enum { PD_EXPLICIT = 0,   /* integrate_explicit,                      basepop.py:658-688      */
+       PD_TAU_LEAP = 1,   /* integrate_discrete_time_stochastic,      basepop.py:797-852      */
+       PD_GILLESPIE = 2 };/* integrate_continuous_time_stochastic,    basepop.py:737-795      */
+/* output selector */
+enum { PD_FULL = 0,       /* soln [T][C][M] fp64 (the reference's soln_array per member)      */
+       PD_FINAL = 1,      /* final state [C][M] fp64                                          */
+       PD_STATS = 2 };    /* streaming ensemble moments + histograms (stochastic only)        */
+/* uniform source for the stochastic integrators */
+enum { PD_PHILOX = 0,     /* native counter-based Philox4x32-10                               */
+       PD_INJECT = 1 };   /* caller-supplied uniform stream replacing random.random (:174,
+                             :776) and the uniforms inside numpy.random.poisson (:830)        */
+
+typedef struct pd_model pd_model; /* one NVRTC-specialised kernel: (model graph, integrator,
+                                     output, rng, count width, block size)                    */
+
+typedef struct {
+  int32_t method, out_mode, rng_mode;
+  int32_t count_bits;     /* 64 (default) or 32: width of the integer compartment counts      */
+  int32_t block;          /* threads per block, multiple of 32 (0 -> 256)                     */
+  int32_t device;         /* CUDA ordinal                                                     */
+  int32_t n_comp, n_param, n_member_param, n_scaleup, n_flow; /* must match the model header  */
+  int32_t reserved;
+} pd_model_desc;
+
+typedef struct {
+  double kernel_ms;       /* device time of the integrator kernel (CUDA events)               */
+  double h2d_ms, d2h_ms;  /* staging time when host buffers were passed                       */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t n_steps;       /* derivative evaluations / tau-leap steps / Gillespie events, total */
+  int32_t err_code;       /* 0, or the PD_ERR_* code of the first failing member              */
+  int32_t err_where;      /* target index where it was raised (explicit) or 0                 */
+  int64_t err_member;     /* global member id                                                 */
+  int32_t grid, block, regs_per_thread, smem_bytes, blocks_per_sm, n_launch;
+} pd_run_result;
+
+/* Inputs common to the stochastic runs.  y0: [C] (shared, y0_per_member = 0) or [C][M].
+ * member_params: [n_member_param][M].  target_times: the host grid produced by make_times
+ * (basepop.py:355-376).                                                                      */
+typedef struct {
+  int64_t n_member, member0;
+  const double *y0; int32_t y0_per_member, n_time;
+  const double *uniform_params;   /* [n_param] HOST: values of all parameter slots            */
+  const double *member_params;
+  const double *target_times;     /* [n_time] HOST                                            */
+  uint64_t seed;
+  const double *uniforms; int64_t n_uniform;           /* PD_INJECT: [n_uniform][M]           */
+  double *soln;                   /* PD_FULL  [T][C][M]                                       */
+  double *final_state;            /* PD_FINAL [C][M]                                          */
+  uint64_t *moments;              /* PD_STATS [T][C][2], ACCUMULATED into (caller zeroes)     */
+  uint32_t *hist;                 /* PD_STATS [n_hist_row][C][hist_bins] or NULL, accumulated */
+  const int32_t *hist_row;        /* [T] HOST: row per target index or -1                     */
+  const int32_t *hist_shift;      /* [C] HOST: bin = min(count >> shift, bins - 1)            */
+  int32_t hist_bins, n_hist_row;
+  void *stream;                   /* cudaStream_t or NULL                                     */
+} pd_stoch_run;
+
+typedef struct {
+  int64_t n_member;
+  const double *y0; int32_t y0_per_member, n_time;
+  const double *uniform_params;   /* [n_param] HOST                                           */
+  const double *member_params;    /* [n_member_param][M]                                      */
+  const int32_t *n_sub;           /* [T-1] HOST   } from pd_explicit_schedule                 */
+  const double *dt;               /* [n_steps] HOST                                           */
+  const double *t_eval;           /* [n_steps] HOST (may be NULL when the model ignores time) */
+  const double *scaleup_table;    /* [n_steps][n_scaleup] HOST or NULL                        */
+  int64_t n_steps;
+  double *soln;                   /* PD_FULL  [T][C][M]                                       */
+  double *final_state;            /* PD_FINAL [C][M]                                          */
+  void *stream;
+} pd_explicit_run;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int pd_version(void);
+const char *pd_last_error(void);
+int pd_device_count(void);
+/* sizeof() of the ABI structs as compiled: 0 pd_model_desc, 1 pd_run_result, 2 pd_stoch_run,
+ * 3 pd_explicit_run -- lets a foreign-language binding verify its struct layout.              */
+int pd_struct_size(int which);
+
+/* ---- flow compiler back end -------------------------------------------------------------- */
+/* Compile the generated model header (popdynamics_b200/codegen.py) together with the
+ * hand-written kernel for desc->method.  Needs no GPU (NVRTC only).  Replaces nothing in the
+ * reference: it is the lowering of set_flows()/calculate_vars() (basepop.py:553, :628).       */
+int pd_model_create(const char *model_header, const pd_model_desc *desc, pd_model **out);
+void pd_model_destroy(pd_model *m);
+/* size of the sm_100a cubin and, once loaded on a device, registers per thread               */
+int pd_model_cubin_size(const pd_model *m, size_t *bytes);
+/* copy the cubin (for cuobjdump / offline inspection)                                        */
+int pd_model_cubin_copy(const pd_model *m, void *dst, size_t capacity);
+
+/* ---- host helper: sub-step schedule of integrate_explicit, basepop.py:672-682 ------------- */
+/* Fills up to `cap` entries of t_eval / dt (any may be NULL) and n_sub[n_time-1]; returns the
+ * total number of derivative evaluations in *n_steps.                                        */
+int pd_explicit_schedule(int32_t n_time, const double *target_times, double min_dt,
+                         double *t_eval, double *dt, int32_t *n_sub, int64_t cap,
+                         int64_t *n_steps);
+
+/* ---- the three integrators ---------------------------------------------------------------- */
+int pd_run_explicit(pd_model *m, const pd_explicit_run *run, pd_run_result *res);
+int pd_run_tau_leap(pd_model *m, const pd_stoch_run *run, pd_run_result *res);
+int pd_run_gillespie(pd_model *m, const pd_stoch_run *run, pd_run_result *res);
+
+/* ---- ensemble statistics ------------------------------------------------------------------ */
+/* Quantiles from (all-reduced) histograms: for every (row, c) and every q the smallest bin b with
+ * cumulative count >= q * total (inverted CDF); value = b << shift[c].  hist / out may be host
+ * or device.  out: [n_row][C][n_q] int64.                                                    */
+int pd_hist_quantiles(const uint32_t *hist, int32_t n_row, int32_t n_comp, int32_t n_bins,
+                      const int32_t *hist_shift, const double *q, int32_t n_q, int64_t *out,
+                      int32_t device, void *stream);
+
+/* ---- device utilities --------------------------------------------------------------------- */
+/* Fill out[n][M] with the Philox uniforms member (member0 + j) would draw: the same stream the
+ * integrators consume (tests, and device-side generation of injected streams).               */
+int pd_philox_fill(double *out, int64_t n, int64_t n_member, int64_t member0, uint64_t seed,
+                   int32_t device, void *stream);
+/* Pipe-peak microbenchmarks for the roofline denominators MEASURED_PEAKS.json lacks:
+ * kind 0 = fp64 DADD+DMUL (non-fused, what --fmad=false code issues), 1 = fp64 DFMA,
+ * 2 = int32 IMAD/LOP3 mix as in Philox.  Returns giga-operations per second.                  */
+int pd_microbench(int32_t kind, int32_t device, double *gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,71 @@
+/*
+ * pd_args.h -- launch descriptors shared by the host C-ABI (csrc/popdyn_capi.cu) and the device
+ * kernels (compiled by NVRTC).  Plain C, fixed layout: only 8-byte members first, then 4-byte
+ * members in pairs, so host and device agree without packing pragmas.  The model-specific uniform
+ * parameter block (PdUniform, generated) is appended AFTER this fixed part in the kernel argument.
+ */
+#ifndef PD_ARGS_H
+#define PD_ARGS_H
+
+#define PD_OUT_FULL 0   /* soln  [T][C][M] fp64, member fastest (coalesced stores)              */
+#define PD_OUT_FINAL 1  /* final [C][M] fp64                                                     */
+#define PD_OUT_STATS 2  /* streaming moments u64 [T][C][2] + histograms u32 [rows][C][bins]      */
+
+#define PD_RNG_PHILOX 0 /* Philox4x32-10, key = seed, counter = (draw block, global member id)   */
+#define PD_RNG_INJECT 1 /* uniforms[n_uniform][M] fp64 consumed in order (parity tests)          */
+
+#define PD_METHOD_EXPLICIT 0
+#define PD_METHOD_TAU_LEAP 1
+#define PD_METHOD_GILLESPIE 2
+
+#define PD_MAX_HIST_COMP 64
+
+/* error codes (also oracle/popdyn_oracle.h) */
+#define PD_ERR_CHECKS 1        /* checks() assertion failed -> AssertionError on the host        */
+#define PD_ERR_POISSON_MEAN 2  /* negative / NaN Poisson mean (numpy raises ValueError)          */
+#define PD_ERR_ZERO_RATE 3     /* total event rate 0 with events present (ZeroDivisionError)     */
+#define PD_ERR_STREAM 4        /* injected uniform stream exhausted                              */
+#define PD_ERR_LOG0 5          /* log(0) in the waiting time (math domain error)                 */
+#define PD_ERR_COUNT_RANGE 6   /* count too large for the statistics accumulators                */
+
+typedef struct {
+  long long n_member;          /* members in this launch                                         */
+  long long member0;           /* global id of member 0 (Philox counter; shard invariance)       */
+  const double *y0;            /* initial compartments                                           */
+  long long y0_stride_c;       /* element stride between compartments                            */
+  long long y0_stride_m;       /* element stride between members (0 = shared)                    */
+  const double *pm;            /* per-member parameters [PD_NPM][M]                              */
+  const double *target;        /* target times [T]                                               */
+  unsigned long long seed;
+  const double *uniforms;      /* injected stream [n_uniform][M] or NULL                         */
+  long long n_uniform;
+  double *soln;                /* FULL                                                           */
+  double *final_state;         /* FINAL                                                          */
+  unsigned long long *moments; /* STATS: [T][C][2] (sum x, sum x^2), exact integers              */
+  unsigned int *hist;          /* STATS: [n_hist_row][C][hist_bins] or NULL                      */
+  const int *hist_row;         /* [T]: histogram row recorded at each target index, -1 = none    */
+  unsigned long long *n_steps; /* total steps / events executed (atomic)                         */
+  int *err;                    /* [4]: code, member lo, member hi, target index                  */
+  int n_time;
+  int hist_bins;               /* even; 0 = no histograms                                        */
+  int hist_shift[PD_MAX_HIST_COMP]; /* bin = min(count >> shift[c], bins - 1)                    */
+} PdStochArgs;
+
+typedef struct {
+  long long n_member;
+  const double *y0;
+  long long y0_stride_c;
+  long long y0_stride_m;
+  const double *pm;            /* per-member parameters [PD_NPM][M]                              */
+  const int *n_sub;            /* [T-1] sub-steps per target interval (host replay of :675-682)  */
+  const double *dt;            /* [n_steps] step size of every sub-step                          */
+  const double *t_eval;        /* [n_steps] evaluation times (only read when PD_USES_TIME)       */
+  const double *su_table;      /* [n_steps][PD_NSU] scale-up values (host-evaluated closures)    */
+  double *soln;                /* FULL  [T][C][M]                                                */
+  double *final_state;         /* FINAL [C][M]                                                   */
+  int *err;
+  int n_time;
+  int pad;
+} PdExplicitArgs;
+
+#endif

@@ -1,0 +1,194 @@
+/*
+ * pd_gillespie.cuh -- continuous-time stochastic integrator (Gillespie direct method), one
+ * thread per ensemble member, integer compartment counts in registers.
+ *
+ * Restates /root/reference/basepop.py:737-795 and pick_event (:161-178):
+ *   while time < target[i]:
+ *     rates from the current counts (calculate_vars + calculate_events, :763-765)
+ *     no live event  -> dt = target[i] - time                               (:767-770)
+ *     else uniform #1 picks the event: sequential cumulative sum over the LIVE events in
+ *          flow-table order, i = u1 * total, first k with not (i > cumul[k]), else the last
+ *          live event (:168-177); uniform #2 gives dt = -log(u2) / sum(rates)  (:775-776);
+ *          the event is applied BEFORE time advances                        (:778-790)
+ *   the counts recorded at target[i] therefore contain the overshooting event; time is never
+ *   snapped back.
+ * `sum(rates)` is Python's builtin: Neumaier-compensated on CPython >= 3.12 (PD_NAIVE_SUM 0) or
+ * the plain left fold (PD_NAIVE_SUM 1), in which case it equals the last cumulative sum.
+ *
+ * Divergence: in FULL / FINAL mode every lane walks its own target index (flattened loop), so a
+ * warp only idles at the very end of the longest member; STATS mode synchronises the block at
+ * every target time because the statistics are reduced block-wide.
+ */
+#include "pd_model.h"
+#include "pd_common.cuh"
+
+struct PdGilLaunch {
+  PdStochArgs a;
+  PdUniform U;
+};
+
+/* one reaction: returns the error code (0 = ok); advances time, mutates y */
+__device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const double (&pm)[PD_NPM_DIM],
+                                                  pd_count (&y)[PD_C], double &time,
+                                                  const double new_time, PdRng &rng,
+                                                  pd_u64 &n_event) {
+  double yd[PD_C], r[PD_NFLOW_DIM], cumul[PD_NFLOW_DIM];
+#pragma unroll
+  for (int c = 0; c < PD_C; ++c) yd[c] = (double)y[c];
+  pd_event_rates(yd, U, pm, time, (const double *)0, r);
+
+  /* pass 1: cumulative intervals over the live events + Python's sum() */
+  double cum = 0.0;            /* cumul_interval, :170-173                      */
+  double f = 0.0, comp = 0.0;  /* sum(): running value and Neumaier compensation */
+  bool any = false;            /* a live event has been seen                     */
+  bool on_float_path = false;  /* sum() has met its first float                  */
+  int last = -1;
+#define PD_ACC(e, is_int)                                                            \
+  {                                                                                  \
+    cum += r[e]; cumul[e] = cum; last = e; any = true;                               \
+    if (PD_NAIVE_SUM) { /* total == cum */ }                                         \
+    else if (is_int) f += r[e];                                                      \
+    else if (!on_float_path) { f = f + r[e]; on_float_path = true; }                 \
+    else {                                                                           \
+      const double t = f + r[e];                                                     \
+      if (fabs(f) >= fabs(r[e])) comp += (f - t) + r[e]; else comp += (r[e] - t) + f;\
+      f = t;                                                                         \
+    }                                                                                \
+  }
+#define PD_G1_ENTRY(e, to, is_int) PD_ACC(e, is_int)
+#define PD_G1_TRANSFER(e, from, to) if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
+#define PD_G1_DEATH(e, from) if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
+  PD_FOR_EACH_FLOW(PD_G1_ENTRY, PD_G1_TRANSFER, PD_G1_DEATH)
+#undef PD_G1_ENTRY
+#undef PD_G1_TRANSFER
+#undef PD_G1_DEATH
+#undef PD_ACC
+
+  if (!any) {                                   /* :767-770 */
+    const double dt = new_time - time;
+    time += dt;
+    return 0;
+  }
+  const double u1 = rng.next();                 /* :773 -> :174 */
+  const double point = u1 * cum;
+  double total;
+  if (PD_NAIVE_SUM) total = cum;
+  else {
+    total = f;
+    if (on_float_path && comp != 0.0 && pd_isfinite(comp)) total = f + comp;
+  }
+  const double u2 = rng.next();                 /* :776 */
+  if (rng.exhausted) return PD_ERR_STREAM;
+  if (total == 0.0) return PD_ERR_ZERO_RATE;
+  if (u2 == 0.0) return PD_ERR_LOG0;
+  const double dt = -log(u2) / total;
+
+  /* pass 2: first live event with not (point > cumul), else the last live one (:176-177) */
+  int sel = -1;
+#define PD_PICK(e) if (sel < 0 && cumul[e] >= 0.0 && !(point > cumul[e])) sel = e;
+#define PD_G2_ENTRY(e, to, is_int) if (sel < 0 && !(point > cumul[e])) sel = e;
+#define PD_G2_TRANSFER(e, from, to) PD_PICK(e)
+#define PD_G2_DEATH(e, from) PD_PICK(e)
+  PD_FOR_EACH_FLOW(PD_G2_ENTRY, PD_G2_TRANSFER, PD_G2_DEATH)
+#undef PD_G2_ENTRY
+#undef PD_G2_TRANSFER
+#undef PD_G2_DEATH
+#undef PD_PICK
+  if (sel < 0) sel = last;
+
+  /* apply +-1 (:778-787) */
+#define PD_G3_ENTRY(e, to, is_int) if (sel == e) y[to] += 1;
+#define PD_G3_TRANSFER(e, from, to) if (sel == e) { y[from] -= 1; y[to] += 1; }
+#define PD_G3_DEATH(e, from) if (sel == e) y[from] -= 1;
+  PD_FOR_EACH_FLOW(PD_G3_ENTRY, PD_G3_TRANSFER, PD_G3_DEATH)
+#undef PD_G3_ENTRY
+#undef PD_G3_TRANSFER
+#undef PD_G3_DEATH
+  time += dt;                                   /* :790 */
+  ++n_event;
+  return 0;
+}
+
+extern "C" __global__ void __launch_bounds__(PD_BLOCK)
+pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
+  const PdStochArgs &a = L.a;
+  const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + threadIdx.x;
+  const bool active = m < a.n_member;
+  const pd_i64 M = a.n_member;
+
+#if PD_OUT_MODE == PD_OUT_STATS
+  __shared__ PdStatsSmem s_stats;
+  extern __shared__ pd_u32 s_hist[];
+  for (int w = threadIdx.x; w < PD_C * (a.hist_bins >> 1); w += PD_BLOCK) s_hist[w] = 0;
+  __syncthreads();
+#endif
+
+  pd_count y[PD_C];
+  double pm[PD_NPM_DIM];
+  PdRng rng;
+  pm[0] = 0.0;
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * M + m];
+#pragma unroll
+    for (int c = 0; c < PD_C; ++c) {
+      const double v = pd_load_y0(a.y0, a.y0_stride_c, a.y0_stride_m, c, m);
+      y[c] = (pd_count)v;                                   /* :747-748 */
+#if PD_OUT_MODE == PD_OUT_FULL
+      a.soln[(size_t)c * M + m] = v;                        /* :755 */
+#endif
+    }
+    rng.init(a, m);
+  } else {
+#pragma unroll
+    for (int c = 0; c < PD_C; ++c) y[c] = 0;
+  }
+
+  int bad = 0;
+  pd_u64 n_event = 0;
+  double time = a.target[0];
+
+#if PD_OUT_MODE == PD_OUT_STATS
+  pd_stats_record(a, s_stats, s_hist, y, active, 0, m);
+  for (int it = 1; it < a.n_time; ++it) {
+    const double new_time = a.target[it];
+    if (active && !bad) {
+      while (time < new_time) {                             /* :762 */
+        bad = pd_gillespie_event(L.U, pm, y, time, new_time, rng, n_event);
+        if (bad) break;
+      }
+    }
+    pd_stats_record(a, s_stats, s_hist, y, active, it, m);
+  }
+#else
+  if (active) {
+    int it = 1;
+    while (it < a.n_time) {
+      const double new_time = a.target[it];
+      if (time < new_time) {                                /* :762 */
+        bad = pd_gillespie_event(L.U, pm, y, time, new_time, rng, n_event);
+        if (bad) break;
+      } else {
+#if PD_OUT_MODE == PD_OUT_FULL
+#pragma unroll
+        for (int c = 0; c < PD_C; ++c)
+          a.soln[((size_t)it * PD_C + c) * M + m] = (double)y[c];   /* :793-795 */
+#endif
+        ++it;
+      }
+    }
+  }
+#endif
+
+  if (active) {
+#if PD_OUT_MODE == PD_OUT_FINAL
+#pragma unroll
+    for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * M + m] = (double)y[c];
+#endif
+    if (bad) pd_raise(a.err, bad, a.member0 + m, 0);
+  }
+  if (a.n_steps) {
+    const pd_u64 warp_events = pd_warp_sum_u64(n_event);
+    if ((threadIdx.x & 31) == 0 && warp_events) atomicAdd(a.n_steps, warp_events);
+  }
+}

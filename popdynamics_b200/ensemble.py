@@ -1,0 +1,347 @@
+# -*- coding: utf-8 -*-
+"""
+Ensemble engine: runs batches of independent ``BaseModel`` members on one B200 through the C-ABI.
+
+``integrate_single``   -- what ``BaseModel.integrate`` calls: one member, full trajectory; the
+                          drop-in replacement of the loops at /root/reference/basepop.py:658-852.
+``integrate_ensemble`` -- additive API (the reference's ensembles are Python ``for`` loops, e.g.
+                          /root/reference/examples/stochastic_strains_model.py:210-218): M members,
+                          per-member parameter / initial-state sweeps, output as full trajectories
+                          ``[T][C][M]``, final states ``[C][M]`` or streaming statistics (exact
+                          integer moments + histograms -> mean / variance / quantiles).
+
+Buffers may be numpy arrays (host: the library stages them, this is the end-to-end path) or torch
+CUDA tensors (resident in HBM, no copies).  Multi-GPU sharding lives in ``distributed.py``.
+"""
+
+import ctypes
+import math
+import random
+
+import numpy
+
+from . import capi, compiler
+
+_KERNEL_CACHE = {}
+_SCHEDULE_CACHE = {}
+
+
+def _kernel_for(cm, method, out_mode, rng_mode, device, count_bits, block):
+    source = cm.cuda_source()
+    key = (source, method, out_mode, rng_mode, device, count_bits, block)
+    kernel = _KERNEL_CACHE.get(key)
+    if kernel is None:
+        kernel = capi.Model(source, method, out_mode, rng_mode, device, cm.n_comp, cm.n_param,
+                            len(cm.member_param_slots()), cm.n_su, cm.n_flow,
+                            count_bits=count_bits, block=block)
+        _KERNEL_CACHE[key] = kernel
+    return kernel
+
+
+def clear_kernel_cache():
+    for kernel in _KERNEL_CACHE.values():
+        kernel.close()
+    _KERNEL_CACHE.clear()
+
+
+def _schedule(target_times, min_dt):
+    key = (tuple(float(t) for t in target_times), float(min_dt))
+    hit = _SCHEDULE_CACHE.get(key)
+    if hit is None:
+        if len(_SCHEDULE_CACHE) > 64:
+            _SCHEDULE_CACHE.clear()
+        hit = capi.explicit_schedule(target_times, min_dt)
+        _SCHEDULE_CACHE[key] = hit
+    return hit
+
+
+def _scaleup_table(model, cm, t_eval):
+    """Values of the model's scale-up closures at every sub-step time: they depend on time only
+    (/root/reference/basepop.py:544-551) and the explicit time grid is the same for every member,
+    so the ORIGINAL Python closures are evaluated on the host -- exact by construction."""
+    if not cm.su_labels:
+        return None
+    table = numpy.empty((len(t_eval), len(cm.su_labels)), dtype=numpy.float64)
+    for k, label in enumerate(cm.su_labels):
+        fn = model.scaleup_fns[label]
+        table[:, k] = [fn(t) for t in t_eval.tolist()]
+    return table
+
+
+def _is_torch(x):
+    return hasattr(x, 'data_ptr')
+
+
+def _member_param_block(cm, n_member, like=None):
+    slots = cm.member_param_slots()
+    if not slots:
+        return None
+    block = numpy.empty((len(slots), n_member), dtype=numpy.float64)
+    for j, k in enumerate(slots):
+        values = cm.param_values[k]
+        if values.size != n_member:
+            raise ValueError('parameter %r has %d entries for %d members'
+                             % (cm.param_labels[k], values.size, n_member))
+        block[j] = values
+    return block
+
+
+def _initial_state(model, y, n_member):
+    """[C] shared or [C][M] per-member initial compartments."""
+    per_member = any(isinstance(v, numpy.ndarray) for v in y)
+    if not per_member:
+        return numpy.asarray([float(v) for v in y], dtype=numpy.float64), 0
+    block = numpy.empty((len(y), n_member), dtype=numpy.float64)
+    for c, v in enumerate(y):
+        block[c] = v
+    return block, 1
+
+
+class EnsembleResult(object):
+    """Outputs of one ensemble launch (arrays are numpy unless torch buffers were supplied)."""
+
+    def __init__(self):
+        self.method = None
+        self.output = None
+        self.labels = []
+        self.times = None
+        self.n_members = 0
+        self.member_offset = 0
+        self.seed = None
+        self.soln = None          # [T][C][M]
+        self.final = None         # [C][M]
+        self.moments = None       # uint64 [T][C][2]
+        self.hist = None          # uint32 [rows][C][bins]
+        self.hist_times = None    # target index of every histogram row
+        self.hist_shift = None
+        self.hist_bins = 0
+        self.device = 0
+        self.info = {}
+
+    # ---- statistics -------------------------------------------------------------------
+    def _moments_host(self):
+        m = self.moments
+        if _is_torch(m):
+            m = m.cpu().numpy()
+        return m.astype(numpy.float64) if m.dtype != numpy.float64 else m
+
+    def mean(self, n_total=None):
+        n = float(n_total or self.n_members)
+        return self._moments_host()[..., 0] / n
+
+    def var(self, n_total=None, ddof=0):
+        n = float(n_total or self.n_members)
+        m = self._moments_host()
+        mean = m[..., 0] / n
+        return (m[..., 1] / n - mean * mean) * (n / (n - ddof))
+
+    def quantiles(self, q):
+        """[rows][C][len(q)] int64: inverted-CDF quantiles from the histograms (exact when the
+        bin width is 1, i.e. ``hist_shift == 0``, and nothing fell into the overflow bin)."""
+        if self.hist is None:
+            raise ValueError('no histograms were recorded')
+        n_row = len(self.hist_times)
+        C = len(self.labels)
+        if _is_torch(self.hist):
+            import torch
+            out = torch.empty((n_row, C, len(q)), dtype=torch.int64, device=self.hist.device)
+        else:
+            out = numpy.empty((n_row, C, len(q)), dtype=numpy.int64)
+        capi.hist_quantiles(self.hist, n_row, C, self.hist_bins, self.hist_shift, q, out,
+                            device=self.device)
+        return out
+
+    def trajectory(self, member):
+        """(T, C) array of one member, the layout of the reference's ``soln_array``."""
+        s = self.soln[:, :, member]
+        return s.cpu().numpy() if _is_torch(s) else numpy.array(s)
+
+
+def _hist_setup(n_time, n_comp, hist_bins, hist_max, hist_times):
+    if hist_bins % 2:
+        raise ValueError('hist_bins must be even')
+    if hist_times is None:
+        hist_times = list(range(n_time))
+    hist_times = [int(t) % n_time for t in hist_times]
+    row = numpy.full(n_time, -1, dtype=numpy.int32)
+    for r, t in enumerate(hist_times):
+        row[t] = r
+    hist_max = numpy.broadcast_to(numpy.asarray(hist_max, dtype=numpy.float64), (n_comp,))
+    shift = numpy.zeros(n_comp, dtype=numpy.int32)
+    for c in range(n_comp):
+        need = (hist_max[c] + 1.0) / hist_bins
+        shift[c] = max(0, int(math.ceil(math.log2(need)))) if need > 1 else 0
+    return row, shift, numpy.asarray(hist_times, dtype=numpy.int32)
+
+
+def run_compiled(model, cm, method, y, target_times, n_members, output='full', seed=0,
+                 member_offset=0, uniforms=None, device=0, count_bits=64, block=256,
+                 hist_bins=0, hist_max=None, hist_times=None, out=None, moments=None,
+                 hist=None, member_params=None, y0=None, stream=None, min_dt=None):
+    """Launch one compiled model.  Returns an EnsembleResult.  ``out`` / ``moments`` / ``hist`` /
+    ``member_params`` / ``y0`` let the caller supply resident (torch CUDA) buffers."""
+    method_code = capi.METHOD_CODES[method]
+    out_code = capi.OUTPUT_CODES[output]
+    rng_code = capi.INJECT if uniforms is not None else capi.PHILOX
+    kernel = _kernel_for(cm, method_code, out_code, rng_code, device, count_bits, block)
+    C, T, M = cm.n_comp, len(target_times), int(n_members)
+    tt = numpy.ascontiguousarray([float(t) for t in target_times], dtype=numpy.float64)
+
+    res = EnsembleResult()
+    res.method, res.output, res.labels = method, output, list(cm.labels)
+    res.times, res.n_members, res.member_offset, res.seed = tt, M, member_offset, seed
+    res.device = device
+
+    if y0 is None:
+        y0, y0_per_member = _initial_state(model, y, M)
+    else:
+        y0_per_member = 1 if (y0.ndim == 2) else 0
+    if member_params is None:
+        member_params = _member_param_block(cm, M)
+    uniform = cm.uniform_params()
+    keep = [tt, y0, member_params, uniform]
+
+    def alloc(shape, dtype):
+        return numpy.empty(shape, dtype=dtype)
+
+    if method == 'explicit':
+        run = capi.ExplicitRun()
+        min_dt = model.explicit_min_dt if min_dt is None else min_dt
+        t_eval, dt, n_sub = _schedule(target_times, min_dt)
+        su = _scaleup_table(model, cm, t_eval)
+        keep += [t_eval, dt, n_sub, su]
+        run.n_member = M
+        run.y0, run.y0_per_member, run.n_time = capi.address(y0), y0_per_member, T
+        run.uniform_params = capi.address(uniform)
+        run.member_params = capi.address(member_params)
+        n_sub_arg = n_sub if len(n_sub) else numpy.zeros(1, dtype=numpy.int32)
+        keep.append(n_sub_arg)
+        run.n_sub, run.dt = capi.address(n_sub_arg), capi.address(dt) if len(dt) else None
+        run.t_eval = capi.address(t_eval) if (cm.uses_time and len(t_eval)) else None
+        run.scaleup_table = capi.address(su) if su is not None and len(su) else None
+        if su is not None and not len(su):
+            run.scaleup_table = capi.address(numpy.zeros((1, cm.n_su)))
+        run.n_steps = len(dt)
+        res.info['last_eval_time'] = float(t_eval[-1]) if len(t_eval) else None
+    else:
+        run = capi.StochRun()
+        run.n_member, run.member0 = M, int(member_offset)
+        run.y0, run.y0_per_member, run.n_time = capi.address(y0), y0_per_member, T
+        run.uniform_params = capi.address(uniform)
+        run.member_params = capi.address(member_params)
+        run.target_times = capi.address(tt)
+        run.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        if uniforms is not None:
+            if tuple(uniforms.shape)[-1] != M:
+                raise ValueError('uniforms must have shape [n_uniform][n_members]')
+            run.uniforms, run.n_uniform = capi.address(uniforms), int(uniforms.shape[0])
+            keep.append(uniforms)
+
+    if output == 'full':
+        res.soln = out if out is not None else alloc((T, C, M), numpy.float64)
+        run.soln = capi.address(res.soln)
+    elif output == 'final':
+        res.final = out if out is not None else alloc((C, M), numpy.float64)
+        run.final_state = capi.address(res.final)
+    else:
+        if method == 'explicit':
+            raise ValueError("output='stats' is defined for the stochastic integrators")
+        res.moments = moments if moments is not None else numpy.zeros((T, C, 2), numpy.uint64)
+        run.moments = capi.address(res.moments)
+        if hist_bins:
+            if hist_max is None:
+                raise ValueError('hist_max (largest expected count per compartment) is needed '
+                                 'with hist_bins; see ensemble.pilot_hist_max')
+            row, shift, rows = _hist_setup(T, C, hist_bins, hist_max, hist_times)
+            res.hist = hist if hist is not None else numpy.zeros((len(rows), C, hist_bins),
+                                                                 numpy.uint32)
+            res.hist_times, res.hist_shift, res.hist_bins = rows, shift, hist_bins
+            keep += [row, shift]
+            run.hist, run.hist_row = capi.address(res.hist), capi.address(row)
+            run.hist_shift = capi.address(shift)
+            run.hist_bins, run.n_hist_row = hist_bins, len(rows)
+    run.stream = stream
+
+    result = capi.run(kernel, run)
+    res.info.update(result.as_dict())
+    del keep
+    return res
+
+
+def raise_device_error(info, method):
+    code = info.get('err_code', 0)
+    if not code:
+        return
+    message = '%s (member %d, target index %d)' % (
+        capi.DEVICE_ERRORS.get(code, 'device error %d' % code), info.get('err_member', -1),
+        info.get('err_where', 0))
+    if code == 1:
+        raise AssertionError(message)          # checks(), basepop.py:1023-1025
+    if code == 2:
+        raise ValueError(message)              # numpy.random.poisson(lam < 0)
+    if code == 3:
+        raise ZeroDivisionError(message)       # basepop.py:776
+    if code == 5:
+        raise ValueError('math domain error: ' + message)
+    raise RuntimeError(message)
+
+
+def integrate_single(model, y, method, is_continue):
+    """One member, full trajectory: the body of ``BaseModel.integrate``."""
+    cm = compiler.compile_model(model, method, is_continue=is_continue)
+    seed = model.seed if model.seed is not None else random.getrandbits(63)
+    res = run_compiled(model, cm, method, y, model.target_times, 1, output='full', seed=seed,
+                       device=model.device)
+    raise_device_error(res.info, method)
+    info = dict(res.info)
+    info['soln'] = numpy.ascontiguousarray(res.soln[:, :, 0])
+    info['seed'] = seed
+    return info
+
+
+def integrate_ensemble(model, method='explicit', n_members=None, output='full', seed=0,
+                       member_offset=0, uniforms=None, device=None, count_bits=64, block=256,
+                       hist_bins=0, hist_max=None, hist_times=None, check=True, **buffers):
+    """
+    Run ``n_members`` independent members of ``model`` (additive API, see module docstring).
+
+    Per-member sweeps: give ``set_param`` / ``set_compartment`` 1-D arrays of length M.  Native
+    Philox streams are keyed by ``(seed, member_offset + i)``: results do not depend on how the
+    members are split over launches or GPUs.  ``uniforms[n][M]`` switches to the injected-stream
+    protocol (parity tests).  Raises the reference's exception types when a member trips the
+    device error flag (AssertionError for ``checks()``).
+    """
+    assert bool(model.target_times), 'Haven\'t set times yet'
+    if method not in capi.METHOD_CODES:
+        raise ValueError('unknown integration method %r' % (method,))
+    model.clear_solns()
+    model.check_flow_transfers()
+    y = model.get_init_list()
+    cm = compiler.compile_model(model, method)
+    implied = cm.n_members_implied()
+    for v in y:
+        if isinstance(v, numpy.ndarray):
+            if implied not in (None, v.size):
+                raise ValueError('per-member arrays have different lengths')
+            implied = v.size
+    if n_members is None:
+        n_members = implied if implied is not None else 1
+    elif implied is not None and implied != n_members:
+        raise ValueError('n_members=%d but per-member arrays have %d entries'
+                         % (n_members, implied))
+    device = model.device if device is None else device
+    res = run_compiled(model, cm, method, y, model.target_times, n_members, output=output,
+                       seed=seed, member_offset=member_offset, uniforms=uniforms, device=device,
+                       count_bits=count_bits, block=block, hist_bins=hist_bins,
+                       hist_max=hist_max, hist_times=hist_times, **buffers)
+    if check:
+        raise_device_error(res.info, method)
+    return res
+
+
+def pilot_hist_max(model, method, n_pilot=2048, seed=12345, margin=1.5, device=None):
+    """Largest count per compartment over a small pilot ensemble, times ``margin``: a bound for
+    ``hist_max`` when nothing better is known."""
+    res = integrate_ensemble(model, method, n_members=n_pilot, output='full', seed=seed,
+                             device=device)
+    return numpy.ceil(res.soln.max(axis=(0, 2)) * margin)

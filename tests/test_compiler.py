@@ -1,0 +1,176 @@
+"""Flow compiler + calculate_vars tracer: flow-table order, dead-code elimination, parameter slots,
+Python's sum() semantics, loud rejection of constructs that cannot be lowered, and NVRTC
+compilation of the generated CUDA for sm_100a (needs no GPU)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from popdynamics_b200 import capi, compiler
+from popdynamics_b200.basepop import BaseModel
+from popdynamics_b200.compiler import TraceError
+
+import helpers
+
+
+def test_strains_flow_table_is_in_canonical_order():
+    # birth; S->I_inv; S->I_res; I_res->R_res; I_inv->R_inv;
+    # 5 background deaths in label order; 2 infection deaths
+    cm = helpers.compiled(helpers.make_model('strains'), 'discrete_time_stochastic')
+    t = cm.flow_table()
+    assert list(t['kind']) == [0, 1, 1, 2, 2, 3, 3, 3, 3, 3, 4, 4]
+    assert list(t['frm']) == [-1, 0, 0, 1, 2, 0, 1, 2, 3, 4, 2, 1]
+    assert list(t['to']) == [0, 2, 1, 3, 4, -1, -1, -1, -1, -1, -1, -1]
+    assert list(t['is_int']) == [1] + [0] * 11          # rate_birth is the Python int 2
+    assert cm.integer_state and not cm.check_nodes
+
+
+def test_dead_code_elimination_drops_unused_population():
+    cm = helpers.compiled(helpers.make_model('sir'), 'explicit')
+    ops = [cm.graph.nodes[n][0] for n in cm.order]
+    assert ops.count('mul') == 1 and 'add' not in ops    # only beta * infectious survives
+    cm = helpers.compiled(helpers.make_model('seird'), 'explicit')
+    assert 'select' in [cm.graph.nodes[n][0] for n in cm.order]   # Neumaier sum feeds rate_birth
+
+
+def test_param_slots_and_member_sweeps():
+    betas = np.linspace(1., 500., 16)
+    m = helpers.make_model('rmit', params={'beta': betas, 'rho': np.linspace(0., 10., 16)})
+    cm = helpers.compiled(m, 'explicit')
+    assert cm.n_members_implied() == 16
+    swept = [cm.param_labels[k] for k in cm.member_param_slots()]
+    assert sorted(swept) == ['beta', 'rho']
+    assert 'pm[' in cm.cuda_source() and np.isnan(cm.uniform_params()).sum() == 2
+    m = helpers.make_model('rmit', params={'beta': betas, 'rho': np.zeros(3)})
+    with pytest.raises(ValueError):
+        helpers.compiled(m, 'explicit').n_members_implied()
+
+
+def test_later_set_param_is_picked_up_at_integrate_time():
+    # rmit_tb_model.py:139-142 sets beta after construction; set_flows re-runs per integrate
+    m = helpers.make_model('rmit', params={'beta': 50.})
+    m.set_param('rho', 0.7)
+    cm = helpers.compiled(m, 'explicit')
+    assert cm.param_values[cm.param_labels.index('rho')] == 0.7
+
+
+class _Weird(BaseModel):
+    def __init__(self, body):
+        BaseModel.__init__(self)
+        self.body = body
+        self.set_compartment('a', 10.)
+        self.set_compartment('b', 0.)
+        self.set_param('k', 0.5)
+
+    def set_flows(self):
+        self.set_var_transfer_rate_flow('a', 'b', 'rate')
+
+    def calculate_vars(self):
+        self.vars['rate'] = self.body(self)
+
+
+@pytest.mark.parametrize('body', [
+    lambda s: s.params['k'] if s.compartments['a'] > 1 else 0.,       # data-dependent branch
+    lambda s: math.exp(s.compartments['a']),                          # math.* on a traced value
+    lambda s: s.compartments['a'] ** 2,                               # pow
+    lambda s: float(s.compartments['a']),                             # scalar conversion
+    lambda s: max(s.compartments['a'], 1.),                           # builtin max -> bool()
+    lambda s: np.sqrt(s.compartments['a']),                           # numpy ufunc
+    lambda s: s.compartments['a'] % 3,                                # modulo
+])
+def test_unsupported_constructs_are_rejected_loudly(body):
+    with pytest.raises(TypeError):
+        helpers.compiled(_Weird(body), 'explicit')
+
+
+def test_supported_arithmetic_matches_python():
+    body = lambda s: abs(-s.compartments['a']) * s.params['k'] / (1. + s.compartments['b']) \
+        - 0.25 + s.time * 0.
+    m = _Weird(body)
+    cm = helpers.compiled(m, 'explicit')
+    assert cm.uses_time
+    om = oracle.OracleModel(cm)
+    values = om.eval_values([10., 3.], time=2.)
+    assert values[om.slot_of[cm.flow_node[0]]] == abs(-10.) * 0.5 / (1. + 3.) - 0.25 + 2. * 0.
+
+
+def test_missing_var_raises_keyerror_like_the_reference():
+    # the stochastic loops never evaluate scale-ups -> KeyError in tb_model
+    with pytest.raises(KeyError, match='program_rate_detect'):
+        helpers.compiled(helpers.make_model('tb'), 'discrete_time_stochastic')
+    helpers.compiled(helpers.make_model('tb'), 'explicit')
+
+
+def test_sum_semantics():
+    vals = [1e16, 1.0, -1e16, 3.0, 1e-3]
+
+    class S(_Weird):
+        def __init__(self):
+            _Weird.__init__(self, None)
+            for i, v in enumerate(vals):
+                self.set_param('p%d' % i, v)
+
+        def calculate_vars(self):
+            self.vars['rate'] = sum(self.params['p%d' % i] for i in range(len(vals)))
+
+    for naive, want in ((False, sum(vals)), (True, sum(np.float64(v) for v in vals))):
+        cm = helpers.compiled(S(), 'explicit', naive_sum=naive)
+        om = oracle.OracleModel(cm)
+        got = om.eval_values([10., 0.])[om.slot_of[cm.flow_node[0]]]
+        assert got == want
+    assert sum(vals) != sum(np.float64(v) for v in vals)   # the two paths really differ
+
+
+def test_custom_checks_are_traced_into_device_assertions():
+    class Checked(_Weird):
+        def checks(self, error_margin=0.1):
+            assert self.compartments['a'] + self.compartments['b'] <= 10. + error_margin
+            assert self.vars['rate'] >= 0.
+
+    cm = helpers.compiled(Checked(lambda s: s.params['k']), 'explicit')
+    assert len(cm.check_nodes) == 2
+    om = oracle.OracleModel(cm)
+    m = Checked(lambda s: s.params['k'])
+    m.make_times(0, 2, 1)
+    _, _, err = om.explicit([10., 0.], m.target_times)
+    assert err == 0
+    _, _, err = om.explicit([10., 5.], m.target_times)
+    assert err == 1
+    with pytest.raises(TraceError):
+        helpers.compiled(Checked(lambda s: s.params['k']), 'continuous_time_stochastic')
+
+
+def test_explicit_schedule_host_logic():
+    tt = list(range(0, 51))
+    t_eval, dt, n_sub = compiler.explicit_schedule(tt)
+    o_eval, o_dt, o_interval = oracle.explicit_schedule(tt)
+    assert np.array_equal(t_eval, o_eval) and np.array_equal(dt, o_dt)
+    assert n_sub.sum() == len(dt) == 1024 and set(n_sub) <= {20, 21}
+    assert np.array_equal(np.repeat(np.arange(1, 51), n_sub), o_interval)
+
+
+@pytest.mark.parametrize('name,method', [
+    ('sir', 'explicit'), ('seird', 'explicit'), ('tb_vacc', 'explicit'), ('rmit', 'explicit'),
+    ('strains', 'discrete_time_stochastic'), ('strains', 'continuous_time_stochastic'),
+    ('seird', 'discrete_time_stochastic'), ('rmit', 'continuous_time_stochastic'),
+])
+def test_generated_cuda_compiles_for_sm_100a(built_library, name, method):
+    cm = helpers.compiled(helpers.make_model(name), method)
+    outs = ('full', 'final') if method == 'explicit' else ('full', 'stats')
+    for out in outs:
+        for rng in ((0,) if method == 'explicit' else (0, 1)):
+            k = capi.Model(cm.cuda_source(), capi.METHOD_CODES[method], capi.OUTPUT_CODES[out],
+                           rng, 0, cm.n_comp, cm.n_param, len(cm.member_param_slots()), cm.n_su,
+                           cm.n_flow)
+            cubin = k.cubin()
+            assert cubin[:4] == b'\x7fELF' and len(cubin) > 4096
+            k.close()
+
+
+def test_nvrtc_errors_surface_with_the_log(built_library):
+    with pytest.raises(capi.PopdynError, match='NVRTC'):
+        capi.Model('#define PD_C 1\nthis is not CUDA\n', 0, 0, 0, 0, 1, 0, 0, 0, 0)
+    cm = helpers.compiled(helpers.make_model('sir'), 'explicit')
+    with pytest.raises(capi.PopdynError, match='stochastic'):
+        capi.Model(cm.cuda_source(), capi.EXPLICIT, capi.STATS, 0, 0, 3, 2, 0, 0, 2)

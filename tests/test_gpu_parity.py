@@ -1,0 +1,324 @@
+"""GPU parity (run on the B200 box): the CUDA kernels, called through the C-ABI, against the CPU
+oracle on the same seeded inputs and against the reference's golden vectors.
+
+Bars: explicit Euler -- bit-exact fp64 (the north-star tolerance is rel 1e-10; --fmad=false and
+preserved program order make it exact); stochastic integrators -- bit-exact integer counts, both
+under an injected uniform stream and with the native Philox streams."""
+import numpy as np
+import pytest
+
+from oracle import make_golden, oracle
+from popdynamics_b200 import capi, ensemble
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+EXPLICIT_RTOL = 1e-10      # north-star tolerance; the assertions below demand exact equality
+
+
+def test_extension_is_loaded_from_the_tree():
+    import os
+    assert os.path.dirname(capi.LIB_PATH).endswith('popdynamics_b200')
+    assert capi.lib().pd_version() == 100 and capi.device_count() >= 1
+
+
+# ------------------------------------------------------------------------------- explicit
+@pytest.mark.parametrize('name,key,times', [
+    ('sir', 'sir_explicit', (0, 50, 1)),
+    ('seir_measles', 'seir_measles_explicit', (0, 200, 1)),
+    ('seir_flu', 'seir_flu_explicit', (0, 200, 1)),
+    ('seird', 'seird_explicit_2000', (0, 2000, 1)),
+    ('rmit', 'rmit_explicit', (0, 500., 1.)),
+    ('strains', 'strains_explicit', (0, 200, 1)),
+])
+def test_dropin_integrate_explicit_matches_reference_golden(golden, name, key, times):
+    m = helpers.make_model(name)
+    m.make_times(*times)
+    m.integrate('explicit')
+    assert m.soln_array.shape == golden[key].shape
+    np.testing.assert_allclose(m.soln_array, golden[key], rtol=EXPLICIT_RTOL, atol=0)
+    assert np.array_equal(m.soln_array, golden[key])
+    assert m.times == m.target_times
+
+
+@pytest.mark.parametrize('name', ['tb', 'tb_vacc'])
+def test_dropin_tb_with_scaleups_and_diagnostics(golden, name):
+    m = helpers.make_model(name)
+    m.make_times(1900, 2050, .05)
+    m.integrate(method='explicit')
+    assert np.array_equal(m.soln_array[::50], golden[name + '_explicit_every50'])
+    assert np.array_equal(m.soln_array[-1], golden[name + '_explicit_final'])
+    # diagnostics pass incl. the stale scale-up quirk
+    assert m.var_labels == list(golden[name + '_var_labels'])
+    assert np.array_equal(m.var_array[::50], golden[name + '_var_array_every50'])
+
+
+def test_dropin_sir_diagnostics_and_vars(golden):
+    m = helpers.make_model('sir')
+    m.make_times(0, 50, 1)
+    m.integrate()
+    assert m.var_labels == list(golden['sir_explicit_var_labels'])
+    assert np.array_equal(m.var_array, golden['sir_explicit_var_array'])
+    assert np.array_equal(m.flow_array, golden['sir_explicit_flow_array'])
+    assert np.array_equal(np.array(m.fraction_soln['immune']),
+                          golden['sir_explicit_fraction_immune'])
+    r = helpers.make_model('rmit')
+    r.make_times(0, 500., 1.)
+    r.integrate(method='explicit')
+    assert r.vars['proportion'] == golden['rmit_proportion'][0]   # rmit_tb_model.py:143
+
+
+def test_dropin_is_continue_chain(golden):
+    m = helpers.make_model('mix', params={'start_population': 100})
+    m.make_times(0, 5, 0.2)
+    m.integrate('explicit')
+    m.make_times(5, 10, 0.2)
+    m.integrate('explicit', is_continue=True)
+    assert np.array_equal(m.soln_array, golden['mix_continue_explicit'])
+    assert np.array_equal(np.array(m.times, dtype=float), golden['mix_continue_times'])
+
+
+def test_explicit_parameter_sweep_matches_oracle_per_member(golden):
+    n = 300
+    rng = np.random.default_rng(0)
+    params = dict(sigma1=rng.uniform(0, .5, n), sigma2=rng.uniform(0, .5, n),
+                  sigma3=rng.uniform(0, .5, n), beta=rng.uniform(1., 500., n),
+                  rho=rng.uniform(0., 10., n), tau=2.)
+    m = helpers.make_model('rmit', params=params)
+    m.make_times(0, 60., 1.)
+    res = m.integrate_ensemble('explicit', output='full')
+    assert res.soln.shape == (61, 6, n)
+    om = oracle.OracleModel(helpers.compiled(m, 'explicit'))
+    want = om.explicit_batch(n, m.get_init_list(), m.target_times)
+    assert want['err'] == 0
+    assert np.array_equal(np.transpose(res.soln, (2, 0, 1)), want['soln'])
+    final = m.integrate_ensemble('explicit', output='final').final
+    assert np.array_equal(final.T, want['final'])
+    # the six golden (beta) points of the reference's own figure-8 sweep
+    betas = golden['rmit_sweep_betas']
+    m = helpers.make_model('rmit', params=dict(sigma1=0.25, sigma2=0.125, sigma3=0.125, tau=2.,
+                                               beta=betas.copy(), rho=0.5))
+    m.make_times(0, 500., 1.)
+    final = m.integrate_ensemble('explicit', output='final').final
+    assert np.array_equal(final.T, golden['rmit_sweep_final'])
+
+
+def test_explicit_per_member_initial_state_and_ragged_sizes():
+    for n in (1, 31, 257):
+        start = np.linspace(1., 40., n)
+        m = helpers.make_model('sir', params={'population': 500.0, 'start_infectious': start})
+        m.make_times(0, 12, 1)
+        res = m.integrate_ensemble('explicit', output='full')
+        om = oracle.OracleModel(helpers.compiled(m, 'explicit'))
+        y0 = np.stack([500.0 - start, start, np.zeros(n)], axis=1)
+        want = om.explicit_batch(n, y0, m.target_times)
+        assert np.array_equal(np.transpose(res.soln, (2, 0, 1)), want['soln'])
+
+
+def test_single_time_point_and_empty_interval():
+    m = helpers.make_model('sir')
+    m.make_times(3, 3, 1)
+    m.integrate()
+    assert m.soln_array.shape == (1, 3) and list(m.soln_array[0]) == [49., 1., 0.]
+
+
+def test_device_checks_raise_assertionerror():
+    class Exploding(helpers.models.SirModel):
+        def calculate_vars(self):
+            helpers.models.SirModel.calculate_vars(self)
+            self.vars['rate_force'] = self.vars['rate_force'] / (self.compartments['immune'] * 0.)
+
+    m = Exploding()
+    m.make_times(0, 3, 1)
+    with pytest.raises(AssertionError):          # NaN compartments fail `>= 0` (basepop.py:1025)
+        m.integrate()
+
+
+# ------------------------------------------------------------------------------- stochastic
+def _inject(method, model_name, n_member, n_uniform, times, seed, params=None):
+    m = helpers.make_model(model_name, **({'params': params} if params else {}))
+    m.make_times(*times)
+    u = np.random.default_rng(seed).random((n_uniform, n_member))
+    res = m.integrate_ensemble(method, n_members=n_member, output='full', uniforms=u)
+    om = oracle.OracleModel(helpers.compiled(m, method))
+    fn = om.tau_leap if method == 'discrete_time_stochastic' else om.gillespie
+    for i in range(n_member):
+        rng = oracle.Rng('inject', uniforms=u[:, i].copy())
+        want, _, err = fn(m.get_init_list(), m.target_times, rng)
+        assert err == 0
+        got = res.soln[:, :, i]
+        assert np.array_equal(got, want), 'member %d differs' % i
+    return res
+
+
+@pytest.mark.parametrize('method', ['discrete_time_stochastic', 'continuous_time_stochastic'])
+def test_injected_stream_bit_exact_strains(method):
+    _inject(method, 'strains', 200, 12000, (0, 100, 1), seed=5)
+
+
+def test_injected_stream_bit_exact_reaches_ptrs_branch():
+    # lam >= 10: PTRS with log / sqrt / loggam on the device
+    _inject('discrete_time_stochastic', 'sir', 96, 6000, (0, 40, 1), seed=6,
+            params={'population': 5000, 'start_infectious': 20.})
+    params = dict(helpers.models.SEIR_PARAMS['measles'], population=20000., start_infectious=10.)
+    _inject('discrete_time_stochastic', 'seird', 64, 20000, (0, 60, 1), seed=7, params=params)
+
+
+def test_injected_stream_golden_runs_of_the_reference(golden):
+    for tag, method, base in (('dts', 'discrete_time_stochastic', 100),
+                              ('cts', 'continuous_time_stochastic', 200)):
+        u = np.stack([make_golden.injected_stream(base + k, 20000) for k in range(4)], axis=1)
+        m = helpers.make_model('strains')
+        m.make_times(0, 150, 1)
+        res = m.integrate_ensemble(method, n_members=4, output='full',
+                                   uniforms=np.ascontiguousarray(u))
+        for k in range(4):
+            assert np.array_equal(res.soln[:, :, k], golden['strains_%s_inject%d' % (tag, k)])
+
+
+def test_exhausted_stream_is_reported():
+    m = helpers.make_model('strains')
+    m.make_times(0, 50, 1)
+    with pytest.raises(RuntimeError, match='exhausted'):
+        m.integrate_ensemble('discrete_time_stochastic', n_members=8, uniforms=np.full((10, 8), .5))
+
+
+def test_device_philox_equals_oracle_philox():
+    out = np.empty((11, 70))
+    capi.philox_fill(out, 11, 70, 1000, 0xDEADBEEFCAFE, device=0)
+    for j in (0, 1, 33, 69):
+        rng = oracle.Rng('philox', seed=0xDEADBEEFCAFE, member=1000 + j)
+        assert [rng.random() for _ in range(11)] == list(out[:, j])
+
+
+@pytest.mark.parametrize('method', ['discrete_time_stochastic', 'continuous_time_stochastic'])
+@pytest.mark.parametrize('count_bits', [64, 32])
+def test_native_philox_bit_exact_against_oracle(method, count_bits):
+    m = helpers.make_model('strains')
+    m.make_times(0, 120, 1)
+    n, seed, offset = 333, 99, 5000
+    res = m.integrate_ensemble(method, n_members=n, output='full', seed=seed,
+                               member_offset=offset, count_bits=count_bits)
+    om = oracle.OracleModel(helpers.compiled(m, method))
+    want = om.stochastic_batch(method, n, m.get_init_list(), m.target_times, seed, member0=offset)
+    assert want['err'] == 0
+    assert np.array_equal(np.transpose(res.soln, (2, 0, 1)), want['soln'])
+    assert res.info['n_steps'] == want['n_steps']
+    final = m.integrate_ensemble(method, n_members=n, output='final', seed=seed,
+                                 member_offset=offset, count_bits=count_bits).final
+    assert np.array_equal(final.T, want['soln'][:, -1, :])
+
+
+def test_shard_invariance_by_global_member_id():
+    m = helpers.make_model('strains')
+    m.make_times(0, 60, 1)
+    whole = m.integrate_ensemble('discrete_time_stochastic', n_members=1000, output='final', seed=7)
+    a = m.integrate_ensemble('discrete_time_stochastic', n_members=400, output='final', seed=7)
+    b = m.integrate_ensemble('discrete_time_stochastic', n_members=600, output='final', seed=7,
+                             member_offset=400)
+    assert np.array_equal(whole.final, np.concatenate([a.final, b.final], axis=1))
+
+
+def test_stochastic_parameter_sweep_per_member():
+    n = 128
+    r0 = np.linspace(2.5, 4.0, n)
+    m = helpers.make_model('strains', params=[('r0_invader', r0)])
+    m.make_times(0, 80, 1)
+    res = m.integrate_ensemble('discrete_time_stochastic', output='full', seed=3)
+    om = oracle.OracleModel(helpers.compiled(m, 'discrete_time_stochastic'))
+    want = om.stochastic_batch('discrete_time_stochastic', n, m.get_init_list(), m.target_times, 3)
+    assert np.array_equal(np.transpose(res.soln, (2, 0, 1)), want['soln'])
+
+
+def test_dropin_integrate_stochastic_single_member():
+    for method in ('discrete_time_stochastic', 'continuous_time_stochastic'):
+        m = helpers.make_model('sir')
+        m.seed = 1234
+        m.make_times(0, 50, 1)
+        m.integrate(method)
+        om = oracle.OracleModel(helpers.compiled(m, method))
+        want = om.stochastic_batch(method, 1, m.get_init_list(), m.target_times, 1234)
+        assert np.array_equal(m.soln_array, want['soln'][0])
+        assert m.soln_array.sum(axis=1).tolist() == [50.] * 51          # closed population
+        assert 'prevalence' in m.var_labels
+
+
+def test_mix_model_hybrid_switching_runs():
+    # examples/mix_model.py:107-136: per-day switching between CTS and explicit via is_continue
+    m = helpers.make_model('mix', params={'start_population': 100})
+    m.seed = 5
+    m.make_times(0, 1, 0.2)
+    m.integrate('continuous_time_stochastic')
+    day = 1
+    while day < 12:
+        method = 'explicit' if min(m.compartments.values()) > 3 else 'continuous_time_stochastic'
+        m.make_times(day, day + 1, 0.2)
+        m.integrate(method=method, is_continue=True)
+        day += 1
+    assert m.soln_array.shape[0] == len(m.times) == 1 + 12 * 5
+    assert np.all(m.soln_array >= 0)
+
+
+# ------------------------------------------------------------------------------- statistics
+@pytest.mark.parametrize('method', ['discrete_time_stochastic', 'continuous_time_stochastic'])
+def test_streaming_statistics_equal_numpy_over_full_trajectories(method):
+    m = helpers.make_model('strains')
+    m.make_times(0, 70, 1)
+    n, seed, bins = 3000, 11, 2048
+    full = m.integrate_ensemble(method, n_members=n, output='full', seed=seed).soln
+    stats = m.integrate_ensemble(method, n_members=n, output='stats', seed=seed, hist_bins=bins,
+                                 hist_max=2047)
+    counts = full.astype(np.int64)                                   # [T][C][M]
+    assert np.array_equal(stats.moments[..., 0].astype(np.int64), counts.sum(axis=2))
+    assert np.array_equal(stats.moments[..., 1].astype(np.int64), (counts ** 2).sum(axis=2))
+    np.testing.assert_allclose(stats.mean(), full.mean(axis=2), rtol=1e-12)
+    np.testing.assert_allclose(stats.var(), full.var(axis=2), rtol=1e-9, atol=1e-9)
+    assert list(stats.hist_shift) == [0] * 5
+    for t in (0, 1, 35, 70):
+        for c in range(5):
+            want = np.bincount(np.minimum(counts[t, c], bins - 1), minlength=bins)
+            assert np.array_equal(stats.hist[t, c], want)
+    q = [0.025, 0.25, 0.5, 0.75, 0.975]
+    quant = stats.quantiles(q)
+    for t in (1, 35, 70):
+        for c in range(5):
+            assert list(quant[t, c]) == list(helpers.inverted_cdf_quantiles(counts[t, c], q))
+
+
+def test_statistics_large_counts_binned_and_subset_of_times():
+    params = dict(helpers.models.SEIR_PARAMS['measles'], population=200000., start_infectious=50.)
+    m = helpers.make_model('seird', params=params)
+    m.make_times(0, 30, 1)
+    n = 700
+    full = m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='full', seed=2).soln
+    stats = m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='stats', seed=2,
+                                 hist_bins=256, hist_max=200100., hist_times=[0, 10, 30])
+    counts = full.astype(np.int64)
+    assert np.array_equal(stats.moments[..., 0].astype(np.int64), counts.sum(axis=2))
+    assert np.array_equal(stats.moments[..., 1].astype(np.int64), (counts ** 2).sum(axis=2))
+    assert stats.hist.shape == (3, 4, 256) and list(stats.hist_times) == [0, 10, 30]
+    shift = stats.hist_shift
+    assert shift[0] == 10                    # (200100 + 1) / 256 -> 2**10 per bin
+    for r, t in enumerate([0, 10, 30]):
+        for c in range(4):
+            want = np.bincount(np.minimum(counts[t, c] >> shift[c], 255), minlength=256)
+            assert np.array_equal(stats.hist[r, c], want)
+
+
+def test_resident_torch_buffers_are_used_in_place():
+    import torch
+    m = helpers.make_model('strains')
+    m.make_times(0, 40, 1)
+    n = 512
+    soln = torch.zeros((41, 5, n), dtype=torch.float64, device='cuda:0')
+    res = m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='full', seed=4,
+                               out=soln)
+    host = m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='full', seed=4)
+    assert res.info['h2d_bytes'] < 4096 and res.info['d2h_bytes'] == 0
+    assert host.info['d2h_bytes'] == 41 * 5 * n * 8
+    assert np.array_equal(soln.cpu().numpy(), host.soln)
+    moments = torch.zeros((41, 5, 2), dtype=torch.int64, device='cuda:0')
+    m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='stats', seed=4,
+                         moments=moments)
+    assert np.array_equal(moments[..., 0].cpu().numpy(), host.soln.sum(axis=2).astype(np.int64))

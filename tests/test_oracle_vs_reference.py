@@ -1,0 +1,101 @@
+"""Live comparison with the UNMODIFIED reference (only where /root/reference exists, i.e. in the
+authoring container; the GPU box relies on tests/golden/).  Also loads the reference's own example
+classes, unmodified, on top of popdynamics_b200.basepop -- the drop-in claim -- and checks that the
+flow compiler lowers them to the same trajectories."""
+import numpy as np
+import pytest
+
+from oracle import oracle, reference
+from popdynamics_b200 import basepop, compiler
+
+import helpers
+
+pytestmark = pytest.mark.skipif(not reference.available(), reason='reference tree not present')
+
+SEIR = helpers.models.SEIR_PARAMS
+
+
+def dropin(script, cls):
+    return reference.example_classes(script, against=basepop)[cls]
+
+
+def run_dropin_explicit(model):
+    model.check_flow_transfers()
+    cm = compiler.compile_model(model, 'explicit')
+    om = oracle.OracleModel(cm)
+    return om.explicit(model.get_init_list(), model.target_times,
+                       su_table=helpers.scaleup_table(model, cm, model.target_times))[0]
+
+
+@pytest.mark.parametrize('script,cls,args,times', [
+    ('sir_model.py', 'SirModel', (), (0, 50, 1)),
+    ('seir_model.py', 'SeirModel', (SEIR['flu'],), (0, 200, 1)),
+    ('seir_model.py', 'SeirDemographyModel', (SEIR['measles'],), (0, 730, 1)),
+    ('stochastic_strains_model.py', 'StrainsModel', (), (0, 100, 1)),
+    ('tb_model.py', 'SimpleTbModel', (['vaccination'],), (1940, 1990, .05)),
+    ('rmit_tb_model.py', 'RmitTbModel', (dict(helpers.RMIT, beta=120.),), (0, 200., 1.)),
+    ('mix_model.py', 'SirModel', ({'start_population': 100},), (0, 20, 0.2)),
+])
+def test_reference_example_classes_run_unmodified_on_the_dropin(script, cls, args, times):
+    theirs = reference.example_classes(script)[cls](*args)
+    theirs.make_times(*times)
+    theirs.integrate('explicit')
+    ours = dropin(script, cls)(*args)
+    ours.make_times(*times)
+    assert ours.target_times == theirs.target_times
+    soln = run_dropin_explicit(ours)
+    assert np.array_equal(soln, theirs.soln_array)
+
+
+@pytest.mark.parametrize('method,kind', [('discrete_time_stochastic', 'numpy'),
+                                         ('continuous_time_stochastic', 'python')])
+def test_reference_strains_class_stochastic_on_the_dropin(method, kind):
+    reference.seed_all(3)
+    theirs = reference.example_classes('stochastic_strains_model.py')['StrainsModel']()
+    theirs.make_times(0, 120, 1)
+    theirs.integrate(method)
+    ours = dropin('stochastic_strains_model.py', 'StrainsModel')()
+    ours.make_times(0, 120, 1)
+    ours.check_flow_transfers()
+    om = oracle.OracleModel(compiler.compile_model(ours, method))
+    fn = om.tau_leap if kind == 'numpy' else om.gillespie
+    soln, _, err = fn(ours.get_init_list(), ours.target_times, oracle.Rng(kind, 3))
+    assert err == 0 and np.array_equal(soln, theirs.soln_array)
+
+
+def test_tb_model_fails_the_same_way_under_stochastic_methods():
+    # KeyError 'program_rate_detect' in the reference, and in the tracer
+    theirs = reference.example_classes('tb_model.py')['SimpleTbModel']()
+    theirs.make_times(1950, 1951, 1.)
+    with pytest.raises(KeyError, match='program_rate_detect'):
+        theirs.integrate('discrete_time_stochastic')
+    ours = dropin('tb_model.py', 'SimpleTbModel')()
+    ours.make_times(1950, 1951, 1.)
+    ours.check_flow_transfers()
+    with pytest.raises(KeyError, match='program_rate_detect'):
+        compiler.compile_model(ours, 'discrete_time_stochastic')
+
+
+def test_golden_file_is_current(golden):
+    # the committed fixtures are what the reference produces today
+    m = reference.example_classes('sir_model.py')['SirModel']()
+    m.make_times(0, 50, 1)
+    m.integrate()
+    assert np.array_equal(m.soln_array, golden['sir_explicit'])
+    assert list(golden['sir_explicit_var_labels']) == m.var_labels
+
+
+def test_injected_uniform_protocol_against_the_reference():
+    from oracle import make_golden
+    u = make_golden.injected_stream(77, 30000)
+    with reference.injected_uniforms(u) as inj:
+        theirs = reference.example_classes('sir_model.py')['SirModel'](
+            {'population': 3000, 'start_infectious': 30.})
+        theirs.make_times(0, 40, 1)
+        theirs.integrate('discrete_time_stochastic')
+    m = helpers.make_model('sir', params={'population': 3000, 'start_infectious': 30.})
+    m.make_times(0, 40, 1)
+    rng = oracle.Rng('inject', uniforms=u)
+    soln, _, err = helpers.oracle_stochastic(m, 'discrete_time_stochastic', rng)
+    assert err == 0 and np.array_equal(soln, theirs.soln_array)
+    assert rng.consumed == inj.rng.consumed
