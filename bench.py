@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""
+Headline benchmark: trajectory-compartment-steps/sec of the multi-strain SIR ensemble
+(BASELINE.json config 3: examples/stochastic_strains_model.py, discrete-time stochastic,
+10^7 members per GPU, make_times(0, 1000, 1), ensemble mean / variance / quantiles).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework, N GPUs (torchrun for N>1)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on host cores
+
+One "step" = one pass of the hot path over the whole ensemble: M members x 1000 tau-leap steps,
+statistics fused, plus (N > 1) the NCCL all-reduce of the integer moments / histograms and the
+quantile kernel.  ``value`` is measured with the statistics buffers resident in HBM, ``e2e``
+through the public Python API (``BaseModel.integrate_ensemble``) with host numpy buffers.
+Prints ONE JSON line on rank 0.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'trajectory_compartment_steps_per_sec'
+T_END = 1000
+QUANTILES = [0.025, 0.25, 0.5, 0.75, 0.975]
+HIST_BINS = 2048
+HIST_MAX = 2047          # strains counts stay well below 2048 (S ~ 1000-2000): width-1 bins
+# algorithmic operation counts ("roofline"): per Philox4x32-10 block
+# 10 rounds x (2 mul.hi + 2 mul.lo + 2 xor3 + 2 key adds) = 80 int32 ops -> 2 doubles,
+# + 4 int32 ops to pack each 53-bit double
+INT_OPS_PER_PHILOX_BLOCK = 80 + 2 * 4
+
+
+def make_model():
+    from examples import models
+    model = models.StrainsModel()
+    model.make_times(0, T_END, 1)
+    return model
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.device_index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, sm_max, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); sm_max.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(sm_max)),
+                'power_w_max': float(max(power)), 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as handle:
+            return json.load(handle), 'measured'
+    return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_arm(n_member, n_thread=0):
+    """The reference's algorithm on host cores: oracle port (C, OpenMP), same workload."""
+    from oracle import oracle
+    from popdynamics_b200 import compiler
+    model = make_model()
+    model.check_flow_transfers()
+    om = oracle.OracleModel(compiler.compile_model(model, 'discrete_time_stochastic'))
+    t0 = time.perf_counter()
+    out = om.stochastic_batch('discrete_time_stochastic', n_member, model.get_init_list(),
+                              model.target_times, seed=0, want_soln=False, want_moments=True,
+                              n_thread=n_thread)
+    dt = time.perf_counter() - t0
+    assert out['err'] == 0
+    return out['n_steps'] * len(model.labels) / dt, dt, oracle.lib().pdo_max_threads()
+
+
+def sized_cpu_sample(target_seconds):
+    rate, dt, cores = cpu_arm(2000)
+    n_member = max(2000, int(target_seconds * rate / (T_END * 5)))
+    return n_member, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_member, cores = sized_cpu_sample(2.0)
+    for _ in range(args.warmup):
+        cpu_arm(max(500, n_member // 4))
+    t0 = time.perf_counter()
+    total = 0.0
+    for _ in range(args.steps):
+        rate, dt, cores = cpu_arm(n_member)
+        total += n_member * T_END * 5
+    elapsed = time.perf_counter() - t0
+    value = total / elapsed
+    sample = ('%d members x %d tau-leap steps x 5 compartments per step, streaming moments, '
+              'OpenMP over members' % (n_member, T_END))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'comp-steps/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'int64+f64', 'data': 'synthetic',
+        'config': {'workload': 'stochastic_strains_model DTS, make_times(0,1000,1), C=5, '
+                               'bounded sample of the 10^7-member ensemble',
+                   'members_per_step': n_member},
+        'cpu_baseline': {'value': value, 'unit': 'comp-steps/s', 'cores': cores, 'kind': 'port',
+                         'sample': sample,
+                         'note': 'C restatement of basepop.py:797-852 (oracle/popdyn_oracle.c); '
+                                 'the pure-Python reference itself measured 1.09e5 comp-steps/s '
+                                 'per core (BASELINE.md)'},
+        'e2e': {'value': value, 'unit': 'comp-steps/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from popdynamics_b200 import capi, compiler, distributed, ensemble
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    M = args.members
+    start = rank * M                      # weak scaling: every rank owns M members
+    model = make_model()
+    model.check_flow_transfers()
+    model.device = local_rank
+    C, T = len(model.labels), len(model.target_times)
+    cm = compiler.compile_model(model, 'discrete_time_stochastic')
+    y = model.get_init_list()
+
+    n_rows = T
+    moments = torch.zeros((T, C, 2), dtype=torch.int64, device=dev)
+    hist = torch.zeros((n_rows, C, HIST_BINS), dtype=torch.int32, device=dev)
+    quant = torch.empty((n_rows, C, len(QUANTILES)), dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    hist_shift = np.zeros(C, dtype=np.int32)
+
+    def one_step(seed):
+        moments.zero_()
+        hist.zero_()
+        res = ensemble.run_compiled(model, cm, 'discrete_time_stochastic', y, model.target_times,
+                                    M, output='stats', seed=seed, member_offset=start,
+                                    device=local_rank, count_bits=args.count_bits,
+                                    block=args.block, hist_bins=HIST_BINS, hist_max=HIST_MAX,
+                                    moments=moments, hist=hist)
+        ensemble.raise_device_error(res.info, 'discrete_time_stochastic')
+        if world > 1:
+            dist.all_reduce(moments)
+            dist.all_reduce(hist)
+        capi.hist_quantiles(hist, n_rows, C, HIST_BINS, hist_shift, QUANTILES, quant,
+                            device=local_rank)
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        one_step(w)
+    peaks, peak_kind = measured_peaks()
+    int_peak = capi.microbench(2, local_rank)        # G int32 op/s (IMAD / LOP3 mix)
+    fp64_peak = capi.microbench(0, local_rank)       # G fp64 op/s (unfused DMUL + DADD)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    step_ms, kernel_ms, draws = [], [], []
+    info = None
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)                         # evict L2 between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        res = one_step(1000 + k)
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        kernel_ms.append(res.info['kernel_ms'])
+        info = res.info
+    barrier()
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    steps_per_member = T - 1
+    comp_steps_per_step = float(world) * M * steps_per_member * C
+    value = comp_steps_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers (rank-local shard) -------------
+    def e2e_step(seed):
+        res = model.integrate_ensemble('discrete_time_stochastic', n_members=M, output='stats',
+                                       seed=seed, member_offset=start, device=local_rank,
+                                       count_bits=args.count_bits, block=args.block,
+                                       hist_bins=HIST_BINS, hist_max=HIST_MAX)
+        if world > 1:
+            distributed.allreduce_stats(res, device=dev)
+        q = res.quantiles(QUANTILES)
+        mean, var = res.mean(world * M), res.var(world * M)
+        return res, (q, mean, var)
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d = d2h = 0
+    for k in range(e2e_steps):
+        res, _ = e2e_step(2000 + k)
+        h2d, d2h = res.info['h2d_bytes'], res.info['d2h_bytes']
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = comp_steps_per_step * e2e_steps / float(e2e_s.item())
+    d2h += HIST_BINS * 0 + int(np.prod((n_rows, C, len(QUANTILES)))) * 8
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (pd_tau_leap_kernel) ---------------------------
+        k_ms = float(np.mean(kernel_ms))
+        blocks = philox_blocks_per_member(model, cm) * M
+        int_ops = blocks * INT_OPS_PER_PHILOX_BLOCK
+        achieved = int_ops / (k_ms * 1e-3) / 1e9
+        roofline = {
+            'bound': 'int32-alu', 'kernel': 'pd_tau_leap_kernel',
+            'achieved': achieved, 'peak': int_peak, 'unit': 'Gop/s',
+            'frac': achieved / int_peak, 'traffic': None,
+            'peak_source': 'pd_microbench(2) on this GPU (IMAD/LOP3 chain); MEASURED_PEAKS.json '
+                           'has no integer or fp64 entry',
+            'fp64_peak_gops': fp64_peak,
+            'kernel_ms': k_ms, 'share_of_step': k_ms / float(np.mean(step_ms)),
+            'hbm_peak_gbs': peaks.get('hbm_gbs'), 'hbm_peak_kind': peak_kind,
+            'note': 'streaming-statistics mode writes ~0 B/comp-step to HBM; the kernel is bound '
+                    'by the integer pipe (Philox) not by HBM or tensor cores',
+        }
+        cpu_members, cores = sized_cpu_sample(args.cpu_seconds)
+        cpu_value, cpu_dt, cores = cpu_arm(cpu_members)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'comp-steps/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'int%d+f64' % args.count_bits, 'data': 'synthetic',
+            'members_per_sec': float(world) * M * args.steps / (total_ms * 1e-3),
+            'config': {'workload': 'stochastic_strains_model DTS (clamped Poisson tau-leap), '
+                                   'make_times(0,1000,1), C=5, %d members per GPU, streaming '
+                                   'mean/var + %d-bin histograms -> 5 quantiles per (t,c)'
+                                   % (M, HIST_BINS),
+                       'members_per_gpu': M, 'steps_per_member': steps_per_member,
+                       'parallelism': 'members sharded x%d, all-reduce of integer statistics'
+                                      % world,
+                       'l2': 'flushed between timed iterations (256 MiB fill)',
+                       'block': info['block'], 'regs_per_thread': info['regs_per_thread'],
+                       'blocks_per_sm': info['blocks_per_sm']},
+            'roofline': roofline,
+            'cpu_baseline': {'value': cpu_value, 'unit': 'comp-steps/s', 'cores': cores,
+                             'kind': 'port',
+                             'sample': '%d members x 1000 steps x 5 compartments (%.1f s)'
+                                       % (cpu_members, cpu_dt)},
+            'e2e': {'value': e2e_value, 'unit': 'comp-steps/s', 'h2d_bytes_per_step': int(h2d),
+                    'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps},
+            'gpu_launches': 2 * args.steps,
+            'clocks': clocks, 'wall_s': wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def philox_blocks_per_member(model, cm, n_sample=64):
+    """Average number of Philox4x32-10 blocks one member draws over the run (exact for the
+    sampled members: counted by replaying them on the oracle's Philox stream)."""
+    from oracle import oracle
+    om = oracle.OracleModel(cm)
+    total = 0
+    for i in range(n_sample):
+        rng = oracle.Rng('philox', seed=1000, member=i)
+        om.tau_leap(model.get_init_list(), model.target_times, rng)
+        total += int(rng.struct.ctr[0]) + (int(rng.struct.ctr[1]) << 32)
+    return total / float(n_sample)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--members', type=int, default=10**7, help='members per GPU')
+    ap.add_argument('--count-bits', type=int, default=64, choices=[32, 64])
+    ap.add_argument('--block', type=int, default=256)
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -250,13 +250,15 @@ def test_mix_model_hybrid_switching_runs():
     m.seed = 5
     m.make_times(0, 1, 0.2)
     m.integrate('continuous_time_stochastic')
-    day = 1
+    day, expected_rows = 1, len(m.target_times)
     while day < 12:
         method = 'explicit' if min(m.compartments.values()) > 3 else 'continuous_time_stochastic'
-        m.make_times(day, day + 1, 0.2)
+        m.make_times(day, day + 1, 0.2)      # accumulating grid: 5 or 6 points per day
+        expected_rows += len(m.target_times) - 1
         m.integrate(method=method, is_continue=True)
         day += 1
-    assert m.soln_array.shape[0] == len(m.times) == 1 + 12 * 5
+    assert m.soln_array.shape[0] == len(m.times) == expected_rows
+    assert np.all(m.soln_array.sum(axis=1) <= 100.0 + 1e-9)
     assert np.all(m.soln_array >= 0)
 
 
