@@ -211,7 +211,8 @@ def run_gpu_arm(args):
         res = ensemble.run_compiled(model, cm, 'discrete_time_stochastic', y, model.target_times,
                                     M, output='stats', seed=seed, member_offset=start,
                                     device=local_rank, count_bits=args.count_bits,
-                                    block=args.block, hist_bins=HIST_BINS, hist_max=HIST_MAX,
+                                    block=args.block, min_blocks=args.min_blocks,
+                                    hist_bins=HIST_BINS, hist_max=HIST_MAX,
                                     moments=moments, hist=hist)
         ensemble.raise_device_error(res.info, 'discrete_time_stochastic')
         if world > 1:
@@ -268,6 +269,7 @@ def run_gpu_arm(args):
         res = model.integrate_ensemble('discrete_time_stochastic', n_members=M, output='stats',
                                        seed=seed, member_offset=start, device=local_rank,
                                        count_bits=args.count_bits, block=args.block,
+                                       min_blocks=args.min_blocks,
                                        hist_bins=HIST_BINS, hist_max=HIST_MAX)
         if world > 1:
             distributed.allreduce_stats(res, device=dev)
@@ -361,7 +363,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--members', type=int, default=10**7, help='members per GPU')
-    ap.add_argument('--count-bits', type=int, default=64, choices=[32, 64])
+    ap.add_argument('--count-bits', type=int, default=32, choices=[32, 64],
+                    help='width of the integer counts (32: overflow raises the device error flag)')
+    ap.add_argument('--min-blocks', type=int, default=4, help='__launch_bounds__ resident-block cap')
     ap.add_argument('--block', type=int, default=256)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     args = ap.parse_args()

@@ -57,7 +57,8 @@ typedef struct {
   int32_t block;          /* threads per block, multiple of 32 (0 -> 256)                     */
   int32_t device;         /* CUDA ordinal                                                     */
   int32_t n_comp, n_param, n_member_param, n_scaleup, n_flow; /* must match the model header  */
-  int32_t reserved;
+  int32_t min_blocks;     /* __launch_bounds__ second argument: resident blocks per SM the
+                             register allocation must allow (0 -> 1, i.e. no cap)             */
 } pd_model_desc;
 
 typedef struct {

@@ -53,7 +53,7 @@ class PopdynError(RuntimeError):
 class ModelDesc(C.Structure):
     _fields_ = [(name, C.c_int32) for name in
                 ('method', 'out_mode', 'rng_mode', 'count_bits', 'block', 'device', 'n_comp',
-                 'n_param', 'n_member_param', 'n_scaleup', 'n_flow', 'reserved')]
+                 'n_param', 'n_member_param', 'n_scaleup', 'n_flow', 'min_blocks')]
 
 
 class RunResult(C.Structure):
@@ -154,9 +154,9 @@ class Model(object):
     """One NVRTC-specialised kernel (``pd_model``)."""
 
     def __init__(self, header_source, method, out_mode, rng_mode, device, n_comp, n_param,
-                 n_member_param, n_scaleup, n_flow, count_bits=64, block=256):
+                 n_member_param, n_scaleup, n_flow, count_bits=64, block=256, min_blocks=0):
         self.desc = ModelDesc(method, out_mode, rng_mode, count_bits, block, device, n_comp,
-                              n_param, n_member_param, n_scaleup, n_flow, 0)
+                              n_param, n_member_param, n_scaleup, n_flow, min_blocks)
         handle = C.c_void_p()
         check(lib().pd_model_create(header_source.encode(), C.byref(self.desc), C.byref(handle)))
         self.handle = handle

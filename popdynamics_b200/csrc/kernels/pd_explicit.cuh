@@ -21,7 +21,7 @@ struct PdExplicitLaunch {
   PdUniform U;
 };
 
-extern "C" __global__ void __launch_bounds__(PD_BLOCK)
+extern "C" __global__ void __launch_bounds__(PD_BLOCK, PD_MIN_BLOCKS)
 pd_explicit_kernel(const __grid_constant__ PdExplicitLaunch L) {
   const PdExplicitArgs &a = L.a;
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + threadIdx.x;

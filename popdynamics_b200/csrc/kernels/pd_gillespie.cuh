@@ -27,15 +27,25 @@ struct PdGilLaunch {
   PdUniform U;
 };
 
+/* the two uniforms of one reaction: exactly one Philox block when no spare is pending */
+__device__ __forceinline__ void pd_two_uniforms(PdPhilox &rng, double &u1, double &u2) {
+  if (!rng.has_spare) rng.block(u1, u2);
+  else { u1 = rng.next(); u2 = rng.next(); }
+}
+__device__ __forceinline__ void pd_two_uniforms(PdInject &rng, double &u1, double &u2) {
+  u1 = rng.next();
+  u2 = rng.next();
+}
+
 /* one reaction: returns the error code (0 = ok); advances time, mutates y */
 __device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const double (&pm)[PD_NPM_DIM],
                                                   pd_count (&y)[PD_C], double &time,
                                                   const double new_time, PdRng &rng,
                                                   pd_u64 &n_event) {
-  double yd[PD_C], r[PD_NFLOW_DIM], cumul[PD_NFLOW_DIM];
+  double yd[PD_C], mult[PD_NMULT_DIM], r[PD_NFLOW_DIM], cumul[PD_NFLOW_DIM];
 #pragma unroll
   for (int c = 0; c < PD_C; ++c) yd[c] = (double)y[c];
-  pd_event_rates(yd, U, pm, time, (const double *)0, r);
+  pd_event_mults(yd, U, pm, time, (const double *)0, mult);
 
   /* pass 1: cumulative intervals over the live events + Python's sum() */
   double cum = 0.0;            /* cumul_interval, :170-173                      */
@@ -55,9 +65,9 @@ __device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const doub
       f = t;                                                                         \
     }                                                                                \
   }
-#define PD_G1_ENTRY(e, to, is_int) PD_ACC(e, is_int)
-#define PD_G1_TRANSFER(e, from, to) if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
-#define PD_G1_DEATH(e, from) if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
+#define PD_G1_ENTRY(e, to, is_int, rate) r[e] = rate; PD_ACC(e, is_int)
+#define PD_G1_TRANSFER(e, from, to, rate) r[e] = rate; if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
+#define PD_G1_DEATH(e, from, rate) r[e] = rate; if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
   PD_FOR_EACH_FLOW(PD_G1_ENTRY, PD_G1_TRANSFER, PD_G1_DEATH)
 #undef PD_G1_ENTRY
 #undef PD_G1_TRANSFER
@@ -69,7 +79,8 @@ __device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const doub
     time += dt;
     return 0;
   }
-  const double u1 = rng.next();                 /* :773 -> :174 */
+  double u1, u2;                                /* :773 -> :174, then :776 */
+  pd_two_uniforms(rng, u1, u2);
   const double point = u1 * cum;
   double total;
   if (PD_NAIVE_SUM) total = cum;
@@ -77,7 +88,6 @@ __device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const doub
     total = f;
     if (on_float_path && comp != 0.0 && pd_isfinite(comp)) total = f + comp;
   }
-  const double u2 = rng.next();                 /* :776 */
   if (rng.exhausted) return PD_ERR_STREAM;
   if (total == 0.0) return PD_ERR_ZERO_RATE;
   if (u2 == 0.0) return PD_ERR_LOG0;
@@ -86,9 +96,9 @@ __device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const doub
   /* pass 2: first live event with not (point > cumul), else the last live one (:176-177) */
   int sel = -1;
 #define PD_PICK(e) if (sel < 0 && cumul[e] >= 0.0 && !(point > cumul[e])) sel = e;
-#define PD_G2_ENTRY(e, to, is_int) if (sel < 0 && !(point > cumul[e])) sel = e;
-#define PD_G2_TRANSFER(e, from, to) PD_PICK(e)
-#define PD_G2_DEATH(e, from) PD_PICK(e)
+#define PD_G2_ENTRY(e, to, is_int, rate) if (sel < 0 && !(point > cumul[e])) sel = e;
+#define PD_G2_TRANSFER(e, from, to, rate) PD_PICK(e)
+#define PD_G2_DEATH(e, from, rate) PD_PICK(e)
   PD_FOR_EACH_FLOW(PD_G2_ENTRY, PD_G2_TRANSFER, PD_G2_DEATH)
 #undef PD_G2_ENTRY
 #undef PD_G2_TRANSFER
@@ -97,9 +107,9 @@ __device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const doub
   if (sel < 0) sel = last;
 
   /* apply +-1 (:778-787) */
-#define PD_G3_ENTRY(e, to, is_int) if (sel == e) y[to] += 1;
-#define PD_G3_TRANSFER(e, from, to) if (sel == e) { y[from] -= 1; y[to] += 1; }
-#define PD_G3_DEATH(e, from) if (sel == e) y[from] -= 1;
+#define PD_G3_ENTRY(e, to, is_int, rate) if (sel == e) y[to] += 1;
+#define PD_G3_TRANSFER(e, from, to, rate) if (sel == e) { y[from] -= 1; y[to] += 1; }
+#define PD_G3_DEATH(e, from, rate) if (sel == e) y[from] -= 1;
   PD_FOR_EACH_FLOW(PD_G3_ENTRY, PD_G3_TRANSFER, PD_G3_DEATH)
 #undef PD_G3_ENTRY
 #undef PD_G3_TRANSFER
@@ -109,7 +119,7 @@ __device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const doub
   return 0;
 }
 
-extern "C" __global__ void __launch_bounds__(PD_BLOCK)
+extern "C" __global__ void __launch_bounds__(PD_BLOCK, PD_MIN_BLOCKS)
 pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
   const PdStochArgs &a = L.a;
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + threadIdx.x;

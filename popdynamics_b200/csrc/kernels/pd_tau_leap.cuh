@@ -18,9 +18,10 @@ struct PdTauLaunch {
   PdUniform U;
 };
 
-extern "C" __global__ void __launch_bounds__(PD_BLOCK)
+extern "C" __global__ void __launch_bounds__(PD_BLOCK, PD_MIN_BLOCKS)
 pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   const PdStochArgs &a = L.a;
+  const PdUniform &U = L.U;
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + threadIdx.x;
   const bool active = m < a.n_member;
   const pd_i64 M = a.n_member;
@@ -61,41 +62,52 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   for (int it = 1; it < a.n_time; ++it) {
     if (active) {
       const double dt = a.target[it] - a.target[it - 1];    /* :820 */
-      double yd[PD_C], r[PD_NFLOW_DIM];
+      /* start-of-step counts as doubles: every rate of this step is formed from them, the
+       * live counts y[] only enter through the clamps (:824 vs :833-841) */
+      double yd[PD_C], mult[PD_NMULT_DIM];
 #pragma unroll
       for (int c = 0; c < PD_C; ++c) yd[c] = (double)y[c];
-      pd_event_rates(yd, L.U, pm, time, (const double *)0, r);   /* :822-824 */
+      pd_event_mults(yd, U, pm, time, (const double *)0, mult);   /* :822-824 */
 
-#define PD_TAU_ENTRY(e, to, is_int)                                                  \
+/* draws are made in 64 bits; with 32-bit counts a gain that would overflow raises the
+ * error flag instead of wrapping (numpy / Python ints never wrap) */
+#define PD_TAU_GAIN(to, d)                                                           \
   {                                                                                  \
-    const double mean = r[e] * dt;                                                   \
-    if (!(mean >= 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
-    else y[to] += (pd_count)pd_poisson(rng, mean);               /* :842-844 */      \
+    if (sizeof(pd_count) == 4 && (pd_i64)y[to] + (d) > 0x7fffffffLL) {               \
+      if (!bad) bad = PD_ERR_COUNT_RANGE;                                            \
+    } else y[to] += (pd_count)(d);                                                   \
   }
-#define PD_TAU_TRANSFER(e, from, to)                                                 \
-  if (r[e] > 0) {                                                                    \
-    const double mean = r[e] * dt;                                                   \
+#define PD_TAU_ENTRY(e, to, is_int, rate)                                            \
+  {                                                                                  \
+    const double mean = rate * dt;                                                   \
+    if (!(mean >= 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
+    else { const pd_i64 d = pd_poisson(rng, mean); PD_TAU_GAIN(to, d) } /* :842-844 */\
+  }
+#define PD_TAU_TRANSFER(e, from, to, rate)                                           \
+  if (rate > 0) {                                                                    \
+    const double mean = rate * dt;                                                   \
     if (!(mean >= 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
     else {                                                                           \
-      pd_count d = (pd_count)pd_poisson(rng, mean);                                  \
-      if (d > y[from]) d = y[from];                              /* :833-834 */      \
-      y[from] -= d; y[to] += d;                                                      \
+      pd_i64 d = pd_poisson(rng, mean);                                              \
+      if (d > (pd_i64)y[from]) d = (pd_i64)y[from];              /* :833-834 */      \
+      y[from] -= (pd_count)d; PD_TAU_GAIN(to, d)                                     \
     }                                                                                \
   }
-#define PD_TAU_DEATH(e, from)                                                        \
-  if (r[e] > 0) {                                                                    \
-    const double mean = r[e] * dt;                                                   \
+#define PD_TAU_DEATH(e, from, rate)                                                  \
+  if (rate > 0) {                                                                    \
+    const double mean = rate * dt;                                                   \
     if (!(mean >= 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
     else {                                                                           \
-      pd_count d = (pd_count)pd_poisson(rng, mean);                                  \
-      if (d > y[from]) d = y[from];                              /* :839-840 */      \
-      y[from] -= d;                                                                  \
+      pd_i64 d = pd_poisson(rng, mean);                                              \
+      if (d > (pd_i64)y[from]) d = (pd_i64)y[from];              /* :839-840 */      \
+      y[from] -= (pd_count)d;                                                        \
     }                                                                                \
   }
       PD_FOR_EACH_FLOW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
 #undef PD_TAU_ENTRY
 #undef PD_TAU_TRANSFER
 #undef PD_TAU_DEATH
+#undef PD_TAU_GAIN
       time += dt;                                           /* :848 */
 #if PD_OUT_MODE == PD_OUT_FULL
 #pragma unroll

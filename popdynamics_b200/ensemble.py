@@ -26,14 +26,14 @@ _KERNEL_CACHE = {}
 _SCHEDULE_CACHE = {}
 
 
-def _kernel_for(cm, method, out_mode, rng_mode, device, count_bits, block):
+def _kernel_for(cm, method, out_mode, rng_mode, device, count_bits, block, min_blocks=0):
     source = cm.cuda_source()
-    key = (source, method, out_mode, rng_mode, device, count_bits, block)
+    key = (source, method, out_mode, rng_mode, device, count_bits, block, min_blocks)
     kernel = _KERNEL_CACHE.get(key)
     if kernel is None:
         kernel = capi.Model(source, method, out_mode, rng_mode, device, cm.n_comp, cm.n_param,
                             len(cm.member_param_slots()), cm.n_su, cm.n_flow,
-                            count_bits=count_bits, block=block)
+                            count_bits=count_bits, block=block, min_blocks=min_blocks)
         _KERNEL_CACHE[key] = kernel
     return kernel
 
@@ -177,13 +177,15 @@ def _hist_setup(n_time, n_comp, hist_bins, hist_max, hist_times):
 def run_compiled(model, cm, method, y, target_times, n_members, output='full', seed=0,
                  member_offset=0, uniforms=None, device=0, count_bits=64, block=256,
                  hist_bins=0, hist_max=None, hist_times=None, out=None, moments=None,
-                 hist=None, member_params=None, y0=None, stream=None, min_dt=None):
+                 hist=None, member_params=None, y0=None, stream=None, min_dt=None,
+                 min_blocks=0):
     """Launch one compiled model.  Returns an EnsembleResult.  ``out`` / ``moments`` / ``hist`` /
     ``member_params`` / ``y0`` let the caller supply resident (torch CUDA) buffers."""
     method_code = capi.METHOD_CODES[method]
     out_code = capi.OUTPUT_CODES[output]
     rng_code = capi.INJECT if uniforms is not None else capi.PHILOX
-    kernel = _kernel_for(cm, method_code, out_code, rng_code, device, count_bits, block)
+    kernel = _kernel_for(cm, method_code, out_code, rng_code, device, count_bits, block,
+                         min_blocks)
     C, T, M = cm.n_comp, len(target_times), int(n_members)
     tt = numpy.ascontiguousarray([float(t) for t in target_times], dtype=numpy.float64)
 
@@ -301,7 +303,8 @@ def integrate_single(model, y, method, is_continue):
 
 def integrate_ensemble(model, method='explicit', n_members=None, output='full', seed=0,
                        member_offset=0, uniforms=None, device=None, count_bits=64, block=256,
-                       hist_bins=0, hist_max=None, hist_times=None, check=True, **buffers):
+                       hist_bins=0, hist_max=None, hist_times=None, check=True, min_blocks=0,
+                       **buffers):
     """
     Run ``n_members`` independent members of ``model`` (additive API, see module docstring).
 
@@ -333,7 +336,8 @@ def integrate_ensemble(model, method='explicit', n_members=None, output='full', 
     res = run_compiled(model, cm, method, y, model.target_times, n_members, output=output,
                        seed=seed, member_offset=member_offset, uniforms=uniforms, device=device,
                        count_bits=count_bits, block=block, hist_bins=hist_bins,
-                       hist_max=hist_max, hist_times=hist_times, **buffers)
+                       hist_max=hist_max, hist_times=hist_times, min_blocks=min_blocks,
+                       **buffers)
     if check:
         raise_device_error(res.info, method)
     return res
