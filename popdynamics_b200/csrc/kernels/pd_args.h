@@ -49,7 +49,22 @@ typedef struct {
   int n_time;
   int hist_bins;               /* even; 0 = no histograms                                        */
   int hist_shift[PD_MAX_HIST_COMP]; /* bin = min(count >> shift[c], bins - 1)                    */
+  unsigned int philox_rk[20];  /* Philox round keys (k0, k1) of rounds 0..9, filled by the host
+                                  from `seed`: operands straight from the constant bank          */
 } PdStochArgs;
+
+/* Dynamic shared memory of the stochastic kernels, in this order (host and device agree through
+ * these macros):
+ *   tau-leap only: event codes  double   [n_flow][block]
+ *                  live counts  count_t  [n_comp][block]
+ *                  event table  uint32   [n_flow] (padded to 8 bytes)
+ *   PD_OUT_STATS : histograms   uint32   [2][n_comp][hist_bins / 2]  (two step parities)       */
+#define PD_ALIGN8(x) (((x) + 7) & ~(size_t)7)
+#define PD_TAU_SMEM_BYTES(n_flow, n_comp, block, count_bytes)                              \
+  ((size_t)((n_flow) > 0 ? (n_flow) : 1) * (size_t)(block) * 8 +                            \
+   PD_ALIGN8((size_t)(n_comp) * (size_t)(block) * (size_t)(count_bytes)) +                 \
+   PD_ALIGN8((size_t)((n_flow) > 0 ? (n_flow) : 1) * 4))
+#define PD_HIST_SMEM_BYTES(n_comp, hist_bins) ((size_t)2 * (size_t)(n_comp) * (size_t)((hist_bins) / 2) * 4)
 
 typedef struct {
   long long n_member;

@@ -28,17 +28,20 @@ struct PdGilLaunch {
 };
 
 /* the two uniforms of one reaction: exactly one Philox block when no spare is pending */
-__device__ __forceinline__ void pd_two_uniforms(PdPhilox &rng, double &u1, double &u2) {
-  if (!rng.has_spare) rng.block(u1, u2);
-  else { u1 = rng.next(); u2 = rng.next(); }
+__device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdPhilox &rng, double &u1,
+                                                double &u2) {
+  if (!rng.has_spare) rng.block(a, u1, u2);
+  else { u1 = rng.next(a); u2 = rng.next(a); }
 }
-__device__ __forceinline__ void pd_two_uniforms(PdInject &rng, double &u1, double &u2) {
-  u1 = rng.next();
-  u2 = rng.next();
+__device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdInject &rng, double &u1,
+                                                double &u2) {
+  u1 = rng.next(a);
+  u2 = rng.next(a);
 }
 
 /* one reaction: returns the error code (0 = ok); advances time, mutates y */
-__device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const double (&pm)[PD_NPM_DIM],
+__device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const PdUniform &U,
+                                                  const double (&pm)[PD_NPM_DIM],
                                                   pd_count (&y)[PD_C], double &time,
                                                   const double new_time, PdRng &rng,
                                                   pd_u64 &n_event) {
@@ -80,7 +83,7 @@ __device__ __forceinline__ int pd_gillespie_event(const PdUniform &U, const doub
     return 0;
   }
   double u1, u2;                                /* :773 -> :174, then :776 */
-  pd_two_uniforms(rng, u1, u2);
+  pd_two_uniforms(a, rng, u1, u2);
   const double point = u1 * cum;
   double total;
   if (PD_NAIVE_SUM) total = cum;
@@ -129,7 +132,7 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
 #if PD_OUT_MODE == PD_OUT_STATS
   __shared__ PdStatsSmem s_stats;
   extern __shared__ pd_u32 s_hist[];
-  for (int w = threadIdx.x; w < PD_C * (a.hist_bins >> 1); w += PD_BLOCK) s_hist[w] = 0;
+  for (int w = threadIdx.x; w < 2 * PD_C * (a.hist_bins >> 1); w += PD_BLOCK) s_hist[w] = 0;
   __syncthreads();
 #endif
 
@@ -164,7 +167,7 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
     const double new_time = a.target[it];
     if (active && !bad) {
       while (time < new_time) {                             /* :762 */
-        bad = pd_gillespie_event(L.U, pm, y, time, new_time, rng, n_event);
+        bad = pd_gillespie_event(a, L.U, pm, y, time, new_time, rng, n_event);
         if (bad) break;
       }
     }
@@ -176,7 +179,7 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
     while (it < a.n_time) {
       const double new_time = a.target[it];
       if (time < new_time) {                                /* :762 */
-        bad = pd_gillespie_event(L.U, pm, y, time, new_time, rng, n_event);
+        bad = pd_gillespie_event(a, L.U, pm, y, time, new_time, rng, n_event);
         if (bad) break;
       } else {
 #if PD_OUT_MODE == PD_OUT_FULL

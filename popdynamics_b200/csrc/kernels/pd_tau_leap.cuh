@@ -1,6 +1,6 @@
 /*
  * pd_tau_leap.cuh -- discrete-time stochastic integrator (clamped Poisson tau-leap), one thread
- * per ensemble member, integer compartment counts in registers.
+ * per ensemble member.
  *
  * Restates /root/reference/basepop.py:797-852 for a batch of independent members:
  *   per target interval: dt = target[i] - target[i-1]            (:820, ONE step per interval)
@@ -9,6 +9,22 @@
  *   count for transfers and deaths, unclamped for births          (:826-844)
  *   record the counts                                             (:850-852)
  * Non-entry events exist only when rate > 0 (:712, :718, :725, :733); entry events always.
+ * Poisson(mean) is numpy's legacy transform (pd_common.cuh): a zero mean draws nothing, a mean
+ * below 10 multiplies uniforms until the product drops to exp(-mean), PTRS above.
+ *
+ * Shape of one step (this is where the kernel differs from the reference's nested loops, without
+ * changing which uniform goes to which event):
+ *   1. RATE PASS, all lanes in lockstep: every event's mean and its code -- exp(-mean) for the
+ *      multiplication method, -mean for PTRS -- go to shared memory [event][thread]; a bit mask
+ *      remembers which events draw at all.
+ *   2. DRAW LOOP, flattened: the lane walks its OWN live events while the warp walks the uniform
+ *      stream together.  One trip = one Philox block = two uniforms for every lane; each uniform
+ *      either continues the lane's current product or finishes its event (clamp, move, advance
+ *      to the lane's next live event).  The trip count of a warp is the largest TOTAL number of
+ *      uniforms any lane needs in the step, instead of the sum over events of the per-event
+ *      maxima that the nested event-major loop pays.
+ *   3. the live counts sit in shared memory [compartment][thread] (conflict-free whatever event a
+ *      lane is at), so an event's source / destination may be a run-time index.
  */
 #include "pd_model.h"
 #include "pd_common.cuh"
@@ -18,22 +34,41 @@ struct PdTauLaunch {
   PdUniform U;
 };
 
+#if PD_NFLOW <= 32
+typedef pd_u32 pd_mask;
+#define PD_MASK_FIRST(x) (__ffs((int)(x)) - 1)
+#elif PD_NFLOW <= 64
+typedef pd_u64 pd_mask;
+#define PD_MASK_FIRST(x) (__ffsll((long long)(x)) - 1)
+#else
+#error "the tau-leap kernel handles at most 64 flow-table rows"
+#endif
+
+/* event table word: source | destination << 16, 0xffff = none (entry has no source, death no
+ * destination); generated per model as PD_EVENT_TABLE */
+__device__ const pd_u32 pd_event_table[PD_NFLOW_DIM] = PD_EVENT_TABLE;
+
 extern "C" __global__ void __launch_bounds__(PD_BLOCK, PD_MIN_BLOCKS)
 pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   const PdStochArgs &a = L.a;
   const PdUniform &U = L.U;
-  const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + threadIdx.x;
+  const int tid = threadIdx.x;
+  const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + tid;
   const bool active = m < a.n_member;
   const pd_i64 M = a.n_member;
 
+  extern __shared__ double s_dyn[];
+  double *s_code = s_dyn;                                            /* [PD_NFLOW_DIM][PD_BLOCK] */
+  pd_count *s_y = (pd_count *)(s_code + PD_NFLOW_DIM * PD_BLOCK);    /* [PD_C][PD_BLOCK]          */
+  pd_u32 *s_tab = (pd_u32 *)((char *)s_y + PD_ALIGN8(sizeof(pd_count) * PD_C * PD_BLOCK));
 #if PD_OUT_MODE == PD_OUT_STATS
   __shared__ PdStatsSmem s_stats;
-  extern __shared__ pd_u32 s_hist[];
-  for (int w = threadIdx.x; w < PD_C * (a.hist_bins >> 1); w += PD_BLOCK) s_hist[w] = 0;
-  __syncthreads();
+  pd_u32 *s_hist = (pd_u32 *)((char *)s_tab + PD_ALIGN8(sizeof(pd_u32) * PD_NFLOW_DIM));
+  for (int w = tid; w < 2 * PD_C * (a.hist_bins >> 1); w += PD_BLOCK) s_hist[w] = 0;
 #endif
+  for (int e = tid; e < PD_NFLOW_DIM; e += PD_BLOCK) s_tab[e] = pd_event_table[e];
+  __syncthreads();
 
-  pd_count y[PD_C];
   double pm[PD_NPM_DIM];
   PdRng rng;
   pm[0] = 0.0;
@@ -43,7 +78,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #pragma unroll
     for (int c = 0; c < PD_C; ++c) {
       const double v = pd_load_y0(a.y0, a.y0_stride_c, a.y0_stride_m, c, m);
-      y[c] = (pd_count)v;                                   /* int() truncation, :805-806 */
+      s_y[c * PD_BLOCK + tid] = (pd_count)v;                /* int() truncation, :805-806 */
 #if PD_OUT_MODE == PD_OUT_FULL
       a.soln[(size_t)c * M + m] = v;                        /* row 0 = untruncated y, :813 */
 #endif
@@ -51,10 +86,15 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
     rng.init(a, m);
   } else {
 #pragma unroll
-    for (int c = 0; c < PD_C; ++c) y[c] = 0;
+    for (int c = 0; c < PD_C; ++c) s_y[c * PD_BLOCK + tid] = 0;
   }
 #if PD_OUT_MODE == PD_OUT_STATS
-  pd_stats_record(a, s_stats, s_hist, y, active, 0, m);
+  {
+    pd_count y[PD_C];
+#pragma unroll
+    for (int c = 0; c < PD_C; ++c) y[c] = s_y[c * PD_BLOCK + tid];
+    pd_stats_record(a, s_stats, s_hist, y, active, 0, m);
+  }
 #endif
 
   int bad = 0;
@@ -62,73 +102,166 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   for (int it = 1; it < a.n_time; ++it) {
     if (active) {
       const double dt = a.target[it] - a.target[it - 1];    /* :820 */
-      /* start-of-step counts as doubles: every rate of this step is formed from them, the
-       * live counts y[] only enter through the clamps (:824 vs :833-841) */
+
+      /* ---- 1. rate pass (:822-824): start-of-step counts as doubles; every rate of this step
+       * is formed from them, the live counts only enter through the clamps (:833-841) */
       double yd[PD_C], mult[PD_NMULT_DIM];
 #pragma unroll
-      for (int c = 0; c < PD_C; ++c) yd[c] = (double)y[c];
-      pd_event_mults(yd, U, pm, time, (const double *)0, mult);   /* :822-824 */
-
-/* draws are made in 64 bits; with 32-bit counts a gain that would overflow raises the
- * error flag instead of wrapping (numpy / Python ints never wrap) */
-#define PD_TAU_GAIN(to, d)                                                           \
-  {                                                                                  \
-    if (sizeof(pd_count) == 4 && (pd_i64)y[to] + (d) > 0x7fffffffLL) {               \
-      if (!bad) bad = PD_ERR_COUNT_RANGE;                                            \
-    } else y[to] += (pd_count)(d);                                                   \
-  }
+      for (int c = 0; c < PD_C; ++c) yd[c] = (double)s_y[c * PD_BLOCK + tid];
+      pd_event_mults(yd, U, pm, time, (const double *)0, mult);
+      pd_mask live = 0;
+#define PD_TAU_CODE(e, mean)                                                         \
+  if (mean > 0.0) {                                                                  \
+    double code;                                                                     \
+    if (mean >= 10.0) code = -mean; else code = pd_exp_nonpos(-mean);                \
+    s_code[e * PD_BLOCK + tid] = code;                                               \
+    live |= (pd_mask)1 << e;                                                         \
+  } else if (!(mean == 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }
 #define PD_TAU_ENTRY(e, to, is_int, rate)                                            \
-  {                                                                                  \
-    const double mean = rate * dt;                                                   \
-    if (!(mean >= 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
-    else { const pd_i64 d = pd_poisson(rng, mean); PD_TAU_GAIN(to, d) } /* :842-844 */\
-  }
+  { const double mean = rate * dt; PD_TAU_CODE(e, mean) }
 #define PD_TAU_TRANSFER(e, from, to, rate)                                           \
-  if (rate > 0) {                                                                    \
-    const double mean = rate * dt;                                                   \
-    if (!(mean >= 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
-    else {                                                                           \
-      pd_i64 d = pd_poisson(rng, mean);                                              \
-      if (d > (pd_i64)y[from]) d = (pd_i64)y[from];              /* :833-834 */      \
-      y[from] -= (pd_count)d; PD_TAU_GAIN(to, d)                                     \
-    }                                                                                \
-  }
+  { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
 #define PD_TAU_DEATH(e, from, rate)                                                  \
-  if (rate > 0) {                                                                    \
-    const double mean = rate * dt;                                                   \
-    if (!(mean >= 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
-    else {                                                                           \
-      pd_i64 d = pd_poisson(rng, mean);                                              \
-      if (d > (pd_i64)y[from]) d = (pd_i64)y[from];              /* :839-840 */      \
-      y[from] -= (pd_count)d;                                                        \
-    }                                                                                \
-  }
+  { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
       PD_FOR_EACH_FLOW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
 #undef PD_TAU_ENTRY
 #undef PD_TAU_TRANSFER
 #undef PD_TAU_DEATH
-#undef PD_TAU_GAIN
+#undef PD_TAU_CODE
+
+      /* ---- 2. draw loop.  Lane state: remaining live events (lowest bit = current event e),
+       * the current event's code, running product and count */
+      int e = live ? PD_MASK_FIRST(live) : 0;
+      double code = s_code[e * PD_BLOCK + tid];
+      double prod = 1.0;
+      int X = 0;
+
+/* step to the lane's next live event */
+#define PD_TAU_ADVANCE                                                               \
+  live &= live - 1;                                                                  \
+  if (live) {                                                                        \
+    e = PD_MASK_FIRST(live);                                                         \
+    code = s_code[e * PD_BLOCK + tid];                                               \
+    prod = 1.0; X = 0;                                                               \
+  }
+/* finish the current event with the draw X of the multiplication method: clamp to the CURRENT
+ * source count (:833-834, :839-840), move, births unclamped (:842-844).  With 32-bit counts a
+ * gain that would pass 2^31 - 1 raises the error flag instead of wrapping (numpy / Python ints
+ * never wrap): both terms are non-negative, so the unsigned sum cannot wrap itself */
+#define PD_TAU_FINISH_SMALL                                                          \
+  {                                                                                  \
+    const pd_u32 ft = s_tab[e];                                                      \
+    const int from = (int)(ft & 0xffffu), to = (int)(ft >> 16);                      \
+    pd_count d = (pd_count)X;                                                        \
+    if (from != 0xffff) {                                                            \
+      const pd_count have = s_y[from * PD_BLOCK + tid];                              \
+      d = d < have ? d : have;                                                       \
+      s_y[from * PD_BLOCK + tid] = have - d;                                         \
+    }                                                                                \
+    if (to != 0xffff) {                                                              \
+      const pd_count have = s_y[to * PD_BLOCK + tid];                                \
+      if (sizeof(pd_count) == 4) {                                                   \
+        const pd_u32 sum = (pd_u32)have + (pd_u32)d;                                 \
+        if (sum > 0x7fffffffu) { if (!bad) bad = PD_ERR_COUNT_RANGE; }               \
+        else s_y[to * PD_BLOCK + tid] = (pd_count)sum;                               \
+      } else s_y[to * PD_BLOCK + tid] = have + d;                                    \
+    }                                                                                \
+    PD_TAU_ADVANCE                                                                   \
+  }
+/* the same after PTRS, whose draw may exceed 32 bits */
+#define PD_TAU_FINISH_BIG(k_in)                                                      \
+  {                                                                                  \
+    pd_i64 d = (k_in);                                                               \
+    const pd_u32 ft = s_tab[e];                                                      \
+    const int from = (int)(ft & 0xffffu), to = (int)(ft >> 16);                      \
+    if (from != 0xffff) {                                                            \
+      const pd_count have = s_y[from * PD_BLOCK + tid];                              \
+      if (d > (pd_i64)have) d = (pd_i64)have;                                        \
+      s_y[from * PD_BLOCK + tid] = have - (pd_count)d;                               \
+    }                                                                                \
+    if (to != 0xffff) {                                                              \
+      const pd_count have = s_y[to * PD_BLOCK + tid];                                \
+      if (sizeof(pd_count) == 4 && (pd_i64)have + d > 0x7fffffffLL) {                \
+        if (!bad) bad = PD_ERR_COUNT_RANGE;                                          \
+      } else s_y[to * PD_BLOCK + tid] = have + (pd_count)d;                          \
+    }                                                                                \
+    PD_TAU_ADVANCE                                                                   \
+  }
+/* one uniform of the multiplication method */
+#define PD_TAU_MULT(u)                                                               \
+  {                                                                                  \
+    prod *= (u);                                                                     \
+    if (prod > code) X += 1; else PD_TAU_FINISH_SMALL                                \
+  }
+
+      while (live) {
+        if (code < 0.0) {
+          /* PTRS event (mean >= 10): one attempt = the next two uniforms of the same stream,
+           * judged out of line; the lane rejoins the block-wise walk at the next trip */
+          double u, v;
+#if PD_RNG_MODE == PD_RNG_PHILOX
+          {
+            double x0, x1;
+            rng.block(a, x0, x1);
+            if (rng.has_spare) { u = rng.spare; v = x0; rng.spare = x1; }
+            else { u = x0; v = x1; }
+          }
+#else
+          u = rng.next(a);
+          v = rng.next(a);
+          if (rng.exhausted) break;
+#endif
+          const pd_i64 k = pd_poisson_ptrs_attempt(-code, u, v);
+          if (k >= 0) PD_TAU_FINISH_BIG(k)
+          continue;
+        }
+#if PD_RNG_MODE == PD_RNG_PHILOX
+        if (!rng.has_spare) {               /* every lane without a pending spare: one block */
+          double u0;
+          rng.block(a, u0, rng.spare);
+          rng.has_spare = 1;
+          PD_TAU_MULT(u0)
+        }
+        if (live && code >= 0.0) {          /* the block's second uniform, or the pending spare */
+          rng.has_spare = 0;
+          PD_TAU_MULT(rng.spare)
+        }
+#else
+        const double u = rng.next(a);
+        if (rng.exhausted) break;
+        PD_TAU_MULT(u)
+#endif
+      }
+#undef PD_TAU_MULT
+#undef PD_TAU_FINISH_SMALL
+#undef PD_TAU_FINISH_BIG
+#undef PD_TAU_ADVANCE
       time += dt;                                           /* :848 */
 #if PD_OUT_MODE == PD_OUT_FULL
 #pragma unroll
       for (int c = 0; c < PD_C; ++c)
-        a.soln[((size_t)it * PD_C + c) * M + m] = (double)y[c];   /* :850-852 */
+        a.soln[((size_t)it * PD_C + c) * M + m] = (double)s_y[c * PD_BLOCK + tid];   /* :850-852 */
 #endif
     }
 #if PD_OUT_MODE == PD_OUT_STATS
-    pd_stats_record(a, s_stats, s_hist, y, active, it, m);
+    {
+      pd_count y[PD_C];
+#pragma unroll
+      for (int c = 0; c < PD_C; ++c) y[c] = s_y[c * PD_BLOCK + tid];
+      pd_stats_record(a, s_stats, s_hist, y, active, it, m);
+    }
 #endif
   }
 
   if (active) {
 #if PD_OUT_MODE == PD_OUT_FINAL
 #pragma unroll
-    for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * M + m] = (double)y[c];
+    for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * M + m] = (double)s_y[c * PD_BLOCK + tid];
 #endif
     if (!bad && rng.exhausted) bad = PD_ERR_STREAM;
     if (bad) pd_raise(a.err, bad, a.member0 + m, 0);
   }
-  if (threadIdx.x == 0 && a.n_steps) {
+  if (tid == 0 && a.n_steps) {
     const pd_i64 first = (pd_i64)blockIdx.x * PD_BLOCK;
     const pd_i64 here = (M - first < PD_BLOCK) ? (M - first) : PD_BLOCK;
     atomicAdd(a.n_steps, (pd_u64)here * (pd_u64)(a.n_time - 1));
