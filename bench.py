@@ -34,10 +34,17 @@ T_END = 1000
 QUANTILES = [0.025, 0.25, 0.5, 0.75, 0.975]
 HIST_BINS = 2048
 HIST_MAX = 2047          # strains counts stay well below 2048 (S ~ 1000-2000): width-1 bins
-# algorithmic operation counts ("roofline"): per Philox4x32-10 block
-# 10 rounds x (2 mul.hi + 2 mul.lo + 2 xor3 + 2 key adds) = 80 int32 ops -> 2 doubles,
-# + 4 int32 ops to pack each 53-bit double
-INT_OPS_PER_PHILOX_BLOCK = 80 + 2 * 4
+# Roofline unit costs of pd_tau_leap_kernel on this workload (measured with
+# ncu, profiles/r1_tau_leap_stats_ncu_summary.txt): the kernel is bound by SM instruction issue,
+# so the work unit is the thread-instruction.
+#   USEFUL_INST_PER_MEMBER_STEP: predicated-on thread instructions one member-step needs
+#   (smsp__thread_inst_executed_pred_on.sum / member-steps of the captured launch);
+#   HBM bytes per member-step: the streaming-statistics mode reads y0 once and writes nothing per
+#   step; DRAM_BYTES_PER_MEMBER_STEP is dram__bytes_read+write of the same capture per member-step.
+USEFUL_INST_PER_MEMBER_STEP = 1350.0
+DRAM_BYTES_PER_MEMBER_STEP = None
+SM_COUNT = 148
+LANES_PER_SM_PER_CLK = 128          # 4 schedulers x 1 warp instruction x 32 lanes
 
 
 def make_model():
@@ -114,8 +121,12 @@ def measured_peaks():
 
 # ---------------------------------------------------------------------------------------------
 def cpu_arm(n_member, n_thread=0):
-    """The reference's algorithm on host cores: oracle port (C, OpenMP), same workload."""
+    """The reference's algorithm on host cores: oracle port (C, OpenMP), same workload.  All host
+    cores are used whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
     from oracle import oracle
+    if not n_thread:
+        n_thread = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') \
+            else (os.cpu_count() or 1)
     from popdynamics_b200 import compiler
     model = make_model()
     model.check_flow_transfers()
@@ -126,7 +137,7 @@ def cpu_arm(n_member, n_thread=0):
                               n_thread=n_thread)
     dt = time.perf_counter() - t0
     assert out['err'] == 0
-    return out['n_steps'] * len(model.labels) / dt, dt, oracle.lib().pdo_max_threads()
+    return out['n_steps'] * len(model.labels) / dt, dt, n_thread
 
 
 def sized_cpu_sample(target_seconds):
@@ -295,20 +306,32 @@ def run_gpu_arm(args):
     if rank == 0:
         # ---- roofline of the dominant kernel (pd_tau_leap_kernel) ---------------------------
         k_ms = float(np.mean(kernel_ms))
-        blocks = philox_blocks_per_member(model, cm) * M
-        int_ops = blocks * INT_OPS_PER_PHILOX_BLOCK
-        achieved = int_ops / (k_ms * 1e-3) / 1e9
+        member_steps = float(M) * steps_per_member
+        sm_mhz = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz') or 1965.0
+        issue_peak = SM_COUNT * LANES_PER_SM_PER_CLK * sm_mhz * 1e6 / 1e9      # G thread-inst/s
+        achieved = USEFUL_INST_PER_MEMBER_STEP * member_steps / (k_ms * 1e-3) / 1e9
+        hbm_peak = peaks.get('hbm_gbs')
         roofline = {
-            'bound': 'int32-alu', 'kernel': 'pd_tau_leap_kernel',
-            'achieved': achieved, 'peak': int_peak, 'unit': 'Gop/s',
-            'frac': achieved / int_peak, 'traffic': None,
-            'peak_source': 'pd_microbench(2) on this GPU (IMAD/LOP3 chain); MEASURED_PEAKS.json '
-                           'has no integer or fp64 entry',
-            'fp64_peak_gops': fp64_peak,
+            'bound': 'issue', 'kernel': 'pd_tau_leap_kernel',
+            'achieved': achieved, 'peak': issue_peak, 'unit': 'G thread-inst/s',
+            'frac': achieved / issue_peak,
+            'traffic': (DRAM_BYTES_PER_MEMBER_STEP * member_steps
+                        if DRAM_BYTES_PER_MEMBER_STEP is not None else None),
+            'peak_source': '%d SMs x %d lanes/clk x %.0f MHz (median SM clock sampled during the '
+                           'timed region)' % (SM_COUNT, LANES_PER_SM_PER_CLK, sm_mhz),
+            'per_unit': '%.0f useful thread-instructions per member-step (ncu, profiles/)'
+                        % USEFUL_INST_PER_MEMBER_STEP,
             'kernel_ms': k_ms, 'share_of_step': k_ms / float(np.mean(step_ms)),
-            'hbm_peak_gbs': peaks.get('hbm_gbs'), 'hbm_peak_kind': peak_kind,
-            'note': 'streaming-statistics mode writes ~0 B/comp-step to HBM; the kernel is bound '
-                    'by the integer pipe (Philox) not by HBM or tensor cores',
+            'pipe_peaks_gops': {'int32_imad_lop3': int_peak, 'fp64_dmul_dadd': fp64_peak},
+            'hbm': {'algorithmic_bytes_per_member_step': 0.0,
+                    'full_trajectory_bytes_per_member_step': 8.0 * C,
+                    'peak_gbs': hbm_peak, 'peak_kind': peak_kind,
+                    'full_trajectory_ceiling_member_steps_per_s':
+                        (hbm_peak * 1e9 / (8.0 * C)) if hbm_peak else None},
+            'note': 'neither HBM- nor tensor-bound: streaming-statistics mode moves ~0 B per '
+                    'member-step, and even full-trajectory output (8*C B per member-step) has an '
+                    'HBM ceiling ~10x above what the Poisson draws allow; the bound is '
+                    'instruction issue (Philox rounds, fp64 compares, shared-memory bookkeeping)',
         }
         cpu_members, cores = sized_cpu_sample(args.cpu_seconds)
         cpu_value, cpu_dt, cores = cpu_arm(cpu_members)
@@ -343,19 +366,6 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
-def philox_blocks_per_member(model, cm, n_sample=64):
-    """Average number of Philox4x32-10 blocks one member draws over the run (exact for the
-    sampled members: counted by replaying them on the oracle's Philox stream)."""
-    from oracle import oracle
-    om = oracle.OracleModel(cm)
-    total = 0
-    for i in range(n_sample):
-        rng = oracle.Rng('philox', seed=1000, member=i)
-        om.tau_leap(model.get_init_list(), model.target_times, rng)
-        total += int(rng.struct.ctr[0]) + (int(rng.struct.ctr[1]) << 32)
-    return total / float(n_sample)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -365,7 +375,7 @@ def main():
     ap.add_argument('--members', type=int, default=10**7, help='members per GPU')
     ap.add_argument('--count-bits', type=int, default=32, choices=[32, 64],
                     help='width of the integer counts (32: overflow raises the device error flag)')
-    ap.add_argument('--min-blocks', type=int, default=4, help='__launch_bounds__ resident-block cap')
+    ap.add_argument('--min-blocks', type=int, default=3, help='__launch_bounds__ resident-block cap')
     ap.add_argument('--block', type=int, default=256)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     args = ap.parse_args()

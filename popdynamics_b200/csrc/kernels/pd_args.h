@@ -53,18 +53,25 @@ typedef struct {
                                   from `seed`: operands straight from the constant bank          */
 } PdStochArgs;
 
+/* Streaming statistics are reduced once per EPOCH of PD_EPOCH recorded target times: a lane keeps
+ * walking its own trajectory and parks the counts of each recorded time in a shared-memory ring;
+ * at the end of the epoch the block reduces the ring row by row (pd_common.cuh).               */
+#ifndef PD_EPOCH
+#define PD_EPOCH 4
+#endif
+
 /* Dynamic shared memory of the stochastic kernels, in this order (host and device agree through
  * these macros):
- *   tau-leap only: event codes  double   [n_flow][block]
- *                  live counts  count_t  [n_comp][block]
- *                  event table  uint32   [n_flow] (padded to 8 bytes)
- *   PD_OUT_STATS : histograms   uint32   [2][n_comp][hist_bins / 2]  (two step parities)       */
+ *   tau-leap only: event codes  double   [n_row][block]      (n_row = live flow-table rows)
+ *   counts ring                 count_t  [n_slot][n_comp][block]
+ *                               n_slot = PD_EPOCH for PD_OUT_STATS, 1 for tau-leap otherwise,
+ *                               0 for Gillespie otherwise (counts stay in registers)
+ *   tau-leap only: event table  uint32   [n_row] (padded to 8 bytes)                          */
 #define PD_ALIGN8(x) (((x) + 7) & ~(size_t)7)
-#define PD_TAU_SMEM_BYTES(n_flow, n_comp, block, count_bytes)                              \
-  ((size_t)((n_flow) > 0 ? (n_flow) : 1) * (size_t)(block) * 8 +                            \
-   PD_ALIGN8((size_t)(n_comp) * (size_t)(block) * (size_t)(count_bytes)) +                 \
-   PD_ALIGN8((size_t)((n_flow) > 0 ? (n_flow) : 1) * 4))
-#define PD_HIST_SMEM_BYTES(n_comp, hist_bins) ((size_t)2 * (size_t)(n_comp) * (size_t)((hist_bins) / 2) * 4)
+#define PD_CODE_SMEM_BYTES(n_row, block) ((size_t)((n_row) > 0 ? (n_row) : 1) * (size_t)(block) * 8)
+#define PD_RING_SMEM_BYTES(n_slot, n_comp, block, count_bytes)                             \
+  PD_ALIGN8((size_t)(n_slot) * (size_t)(n_comp) * (size_t)(block) * (size_t)(count_bytes))
+#define PD_TAB_SMEM_BYTES(n_row) PD_ALIGN8((size_t)((n_row) > 0 ? (n_row) : 1) * 4)
 
 typedef struct {
   long long n_member;

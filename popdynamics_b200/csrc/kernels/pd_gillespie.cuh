@@ -15,9 +15,10 @@
  * `sum(rates)` is Python's builtin: Neumaier-compensated on CPython >= 3.12 (PD_NAIVE_SUM 0) or
  * the plain left fold (PD_NAIVE_SUM 1), in which case it equals the last cumulative sum.
  *
- * Divergence: in FULL / FINAL mode every lane walks its own target index (flattened loop), so a
- * warp only idles at the very end of the longest member; STATS mode synchronises the block at
- * every target time because the statistics are reduced block-wide.
+ * Divergence: every lane walks its own target index (flattened loop), so in FULL / FINAL mode a
+ * warp only idles at the very end of its longest member; STATS mode parks the counts in a
+ * shared-memory ring and synchronises the block once per epoch of PD_EPOCH target times, where
+ * the ring is reduced row by row (pd_common.cuh).
  */
 #include "pd_model.h"
 #include "pd_common.cuh"
@@ -26,6 +27,12 @@ struct PdGilLaunch {
   PdStochArgs a;
   PdUniform U;
 };
+
+/* the kernel's dynamic shared memory, read by the host after loading the module
+ * (csrc/popdyn_capi.cu) */
+extern "C" __device__ unsigned int pd_smem_bytes =
+    (PD_OUT_MODE == PD_OUT_STATS)
+        ? (unsigned int)PD_RING_SMEM_BYTES(PD_EPOCH, PD_C, PD_BLOCK, sizeof(pd_count)) : 0u;
 
 /* the two uniforms of one reaction: exactly one Philox block when no spare is pending */
 __device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdPhilox &rng, double &u1,
@@ -130,9 +137,10 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
   const pd_i64 M = a.n_member;
 
 #if PD_OUT_MODE == PD_OUT_STATS
-  __shared__ PdStatsSmem s_stats;
-  extern __shared__ pd_u32 s_hist[];
-  for (int w = threadIdx.x; w < 2 * PD_C * (a.hist_bins >> 1); w += PD_BLOCK) s_hist[w] = 0;
+  extern __shared__ double s_dyn[];
+  pd_count *s_ring = (pd_count *)s_dyn;                     /* [PD_EPOCH][PD_C][PD_BLOCK] */
+  const pd_i64 block_member0 = (pd_i64)blockIdx.x * PD_BLOCK;
+  const int n_active = (M - block_member0 < PD_BLOCK) ? (int)(M - block_member0) : PD_BLOCK;
   __syncthreads();
 #endif
 
@@ -162,16 +170,26 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
   double time = a.target[0];
 
 #if PD_OUT_MODE == PD_OUT_STATS
-  pd_stats_record(a, s_stats, s_hist, y, active, 0, m);
-  for (int it = 1; it < a.n_time; ++it) {
-    const double new_time = a.target[it];
-    if (active && !bad) {
-      while (time < new_time) {                             /* :762 */
-        bad = pd_gillespie_event(a, L.U, pm, y, time, new_time, rng, n_event);
-        if (bad) break;
+  /* Epochs of PD_EPOCH target times.  Inside an epoch the (target, event) loops are flattened as
+   * in the other modes: a lane parks its counts in the ring when it crosses a target time and
+   * keeps going, so a warp only waits for its slowest lane once per epoch; then the block
+   * reduces the ring (pd_stats_flush, two barriers inside). */
+  for (int it0 = 0; it0 < a.n_time; it0 += PD_EPOCH) {
+    const int it1 = (it0 + PD_EPOCH < a.n_time) ? it0 + PD_EPOCH : a.n_time;
+    if (active) {
+      int it = it0;
+      while (it < it1) {
+        if (it > 0 && !bad && time < a.target[it]) {        /* :762 */
+          bad = pd_gillespie_event(a, L.U, pm, y, time, a.target[it], rng, n_event);
+        } else {
+#pragma unroll
+          for (int c = 0; c < PD_C; ++c)
+            s_ring[((it - it0) * PD_C + c) * PD_BLOCK + threadIdx.x] = y[c];   /* :793-795 */
+          ++it;
+        }
       }
     }
-    pd_stats_record(a, s_stats, s_hist, y, active, it, m);
+    pd_stats_flush(a, s_ring, it0, it1 - it0, n_active, a.member0 + block_member0);
   }
 #else
   if (active) {

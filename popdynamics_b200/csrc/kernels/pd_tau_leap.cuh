@@ -34,10 +34,10 @@ struct PdTauLaunch {
   PdUniform U;
 };
 
-#if PD_NFLOW <= 32
+#if PD_TAU_NROW <= 32
 typedef pd_u32 pd_mask;
 #define PD_MASK_FIRST(x) (__ffs((int)(x)) - 1)
-#elif PD_NFLOW <= 64
+#elif PD_TAU_NROW <= 64
 typedef pd_u64 pd_mask;
 #define PD_MASK_FIRST(x) (__ffsll((long long)(x)) - 1)
 #else
@@ -45,8 +45,21 @@ typedef pd_u64 pd_mask;
 #endif
 
 /* event table word: source | destination << 16, 0xffff = none (entry has no source, death no
- * destination); generated per model as PD_EVENT_TABLE */
-__device__ const pd_u32 pd_event_table[PD_NFLOW_DIM] = PD_EVENT_TABLE;
+ * destination); generated per model as PD_TAU_EVENT_TABLE over the rows that can fire */
+__device__ const pd_u32 pd_event_table[PD_TAU_NROW_DIM] = PD_TAU_EVENT_TABLE;
+
+/* ring slots: the live counts of target index `it` sit in slot it % PD_NSLOT */
+#if PD_OUT_MODE == PD_OUT_STATS
+#define PD_NSLOT PD_EPOCH
+#else
+#define PD_NSLOT 1
+#endif
+/* the kernel's dynamic shared memory, read by the host after loading the module
+ * (csrc/popdyn_capi.cu) */
+extern "C" __device__ unsigned int pd_smem_bytes =
+    (unsigned int)(PD_CODE_SMEM_BYTES(PD_TAU_NROW, PD_BLOCK) +
+                   PD_RING_SMEM_BYTES(PD_NSLOT, PD_C, PD_BLOCK, sizeof(pd_count)) +
+                   PD_TAB_SMEM_BYTES(PD_TAU_NROW));
 
 extern "C" __global__ void __launch_bounds__(PD_BLOCK, PD_MIN_BLOCKS)
 pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
@@ -58,20 +71,21 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   const pd_i64 M = a.n_member;
 
   extern __shared__ double s_dyn[];
-  double *s_code = s_dyn;                                            /* [PD_NFLOW_DIM][PD_BLOCK] */
-  pd_count *s_y = (pd_count *)(s_code + PD_NFLOW_DIM * PD_BLOCK);    /* [PD_C][PD_BLOCK]          */
-  pd_u32 *s_tab = (pd_u32 *)((char *)s_y + PD_ALIGN8(sizeof(pd_count) * PD_C * PD_BLOCK));
+  double *s_code = s_dyn;                                          /* [PD_TAU_NROW][PD_BLOCK]   */
+  pd_count *s_ring = (pd_count *)((char *)s_dyn + PD_CODE_SMEM_BYTES(PD_TAU_NROW, PD_BLOCK));
+  pd_u32 *s_tab = (pd_u32 *)((char *)s_ring +
+                             PD_RING_SMEM_BYTES(PD_NSLOT, PD_C, PD_BLOCK, sizeof(pd_count)));
 #if PD_OUT_MODE == PD_OUT_STATS
-  __shared__ PdStatsSmem s_stats;
-  pd_u32 *s_hist = (pd_u32 *)((char *)s_tab + PD_ALIGN8(sizeof(pd_u32) * PD_NFLOW_DIM));
-  for (int w = tid; w < 2 * PD_C * (a.hist_bins >> 1); w += PD_BLOCK) s_hist[w] = 0;
+  const pd_i64 block_member0 = (pd_i64)blockIdx.x * PD_BLOCK;
+  const int n_active = (M - block_member0 < PD_BLOCK) ? (int)(M - block_member0) : PD_BLOCK;
 #endif
-  for (int e = tid; e < PD_NFLOW_DIM; e += PD_BLOCK) s_tab[e] = pd_event_table[e];
+  for (int e = tid; e < PD_TAU_NROW_DIM; e += PD_BLOCK) s_tab[e] = pd_event_table[e];
   __syncthreads();
 
   double pm[PD_NPM_DIM];
   PdRng rng;
   pm[0] = 0.0;
+  pd_count *s_y = s_ring;                                   /* slot of target index 0 */
   if (active) {
 #pragma unroll
     for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * M + m];
@@ -84,22 +98,22 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #endif
     }
     rng.init(a, m);
-  } else {
-#pragma unroll
-    for (int c = 0; c < PD_C; ++c) s_y[c * PD_BLOCK + tid] = 0;
   }
 #if PD_OUT_MODE == PD_OUT_STATS
-  {
-    pd_count y[PD_C];
-#pragma unroll
-    for (int c = 0; c < PD_C; ++c) y[c] = s_y[c * PD_BLOCK + tid];
-    pd_stats_record(a, s_stats, s_hist, y, active, 0, m);
-  }
+  if (a.n_time == 1) pd_stats_flush(a, s_ring, 0, 1, n_active, a.member0 + block_member0);
 #endif
 
   int bad = 0;
   double time = a.target[0];
   for (int it = 1; it < a.n_time; ++it) {
+#if PD_NSLOT > 1
+    const int slot = it % PD_NSLOT;
+    const pd_count *s_prev = s_ring + ((slot ? slot : PD_NSLOT) - 1) * (PD_C * PD_BLOCK);
+    s_y = s_ring + slot * (PD_C * PD_BLOCK);
+#else
+    const int slot = 0;
+    const pd_count *s_prev = s_ring;
+#endif
     if (active) {
       const double dt = a.target[it] - a.target[it - 1];    /* :820 */
 
@@ -107,7 +121,13 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
        * is formed from them, the live counts only enter through the clamps (:833-841) */
       double yd[PD_C], mult[PD_NMULT_DIM];
 #pragma unroll
-      for (int c = 0; c < PD_C; ++c) yd[c] = (double)s_y[c * PD_BLOCK + tid];
+      for (int c = 0; c < PD_C; ++c) {
+        const pd_count have = s_prev[c * PD_BLOCK + tid];
+#if PD_NSLOT > 1
+        s_y[c * PD_BLOCK + tid] = have;                     /* this step's slot starts as a copy */
+#endif
+        yd[c] = (double)have;
+      }
       pd_event_mults(yd, U, pm, time, (const double *)0, mult);
       pd_mask live = 0;
 #define PD_TAU_CODE(e, mean)                                                         \
@@ -123,7 +143,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
 #define PD_TAU_DEATH(e, from, rate)                                                  \
   { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
-      PD_FOR_EACH_FLOW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
+      PD_FOR_EACH_TAU_ROW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
 #undef PD_TAU_ENTRY
 #undef PD_TAU_TRANSFER
 #undef PD_TAU_DEATH
@@ -244,12 +264,9 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #endif
     }
 #if PD_OUT_MODE == PD_OUT_STATS
-    {
-      pd_count y[PD_C];
-#pragma unroll
-      for (int c = 0; c < PD_C; ++c) y[c] = s_y[c * PD_BLOCK + tid];
-      pd_stats_record(a, s_stats, s_hist, y, active, it, m);
-    }
+    /* end of an epoch: the block reduces the ring (two barriers inside) */
+    if (slot == PD_NSLOT - 1 || it == a.n_time - 1)   /* block-uniform */
+      pd_stats_flush(a, s_ring, it - slot, slot + 1, n_active, a.member0 + block_member0);
 #endif
   }
 
