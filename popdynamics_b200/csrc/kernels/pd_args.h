@@ -57,7 +57,10 @@ typedef struct {
  * walking its own trajectory and parks the counts of each recorded time in a shared-memory ring;
  * at the end of the epoch the block reduces the ring row by row (pd_common.cuh).               */
 #ifndef PD_EPOCH
-#define PD_EPOCH 4
+#define PD_EPOCH 16      /* warp-synchronous recording (tau-leap): per-warp partial sums      */
+#endif
+#ifndef PD_RING_EPOCH
+#define PD_RING_EPOCH 4  /* lane-asynchronous recording (Gillespie): ring of parked counts    */
 #endif
 
 /* Dynamic shared memory of the stochastic kernels, in this order (host and device agree through

@@ -17,7 +17,7 @@
  *
  * Divergence: every lane walks its own target index (flattened loop), so in FULL / FINAL mode a
  * warp only idles at the very end of its longest member; STATS mode parks the counts in a
- * shared-memory ring and synchronises the block once per epoch of PD_EPOCH target times, where
+ * shared-memory ring and synchronises the block once per epoch of PD_RING_EPOCH target times, where
  * the ring is reduced row by row (pd_common.cuh).
  */
 #include "pd_model.h"
@@ -32,7 +32,7 @@ struct PdGilLaunch {
  * (csrc/popdyn_capi.cu) */
 extern "C" __device__ unsigned int pd_smem_bytes =
     (PD_OUT_MODE == PD_OUT_STATS)
-        ? (unsigned int)PD_RING_SMEM_BYTES(PD_EPOCH, PD_C, PD_BLOCK, sizeof(pd_count)) : 0u;
+        ? (unsigned int)PD_RING_SMEM_BYTES(PD_RING_EPOCH, PD_C, PD_BLOCK, sizeof(pd_count)) : 0u;
 
 /* the two uniforms of one reaction: exactly one Philox block when no spare is pending */
 __device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdPhilox &rng, double &u1,
@@ -138,7 +138,7 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
 
 #if PD_OUT_MODE == PD_OUT_STATS
   extern __shared__ double s_dyn[];
-  pd_count *s_ring = (pd_count *)s_dyn;                     /* [PD_EPOCH][PD_C][PD_BLOCK] */
+  pd_count *s_ring = (pd_count *)s_dyn;                     /* [PD_RING_EPOCH][PD_C][PD_BLOCK] */
   const pd_i64 block_member0 = (pd_i64)blockIdx.x * PD_BLOCK;
   const int n_active = (M - block_member0 < PD_BLOCK) ? (int)(M - block_member0) : PD_BLOCK;
   __syncthreads();
@@ -170,12 +170,12 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
   double time = a.target[0];
 
 #if PD_OUT_MODE == PD_OUT_STATS
-  /* Epochs of PD_EPOCH target times.  Inside an epoch the (target, event) loops are flattened as
+  /* Epochs of PD_RING_EPOCH target times.  Inside an epoch the (target, event) loops are flattened as
    * in the other modes: a lane parks its counts in the ring when it crosses a target time and
    * keeps going, so a warp only waits for its slowest lane once per epoch; then the block
    * reduces the ring (pd_stats_flush, two barriers inside). */
-  for (int it0 = 0; it0 < a.n_time; it0 += PD_EPOCH) {
-    const int it1 = (it0 + PD_EPOCH < a.n_time) ? it0 + PD_EPOCH : a.n_time;
+  for (int it0 = 0; it0 < a.n_time; it0 += PD_RING_EPOCH) {
+    const int it1 = (it0 + PD_RING_EPOCH < a.n_time) ? it0 + PD_RING_EPOCH : a.n_time;
     if (active) {
       int it = it0;
       while (it < it1) {

@@ -1,6 +1,6 @@
 /*
  * pd_tau_leap.cuh -- discrete-time stochastic integrator (clamped Poisson tau-leap), one thread
- * per ensemble member.
+ * per ensemble member, integer compartment counts in registers.
  *
  * Restates /root/reference/basepop.py:797-852 for a batch of independent members:
  *   per target interval: dt = target[i] - target[i-1]            (:820, ONE step per interval)
@@ -12,19 +12,20 @@
  * Poisson(mean) is numpy's legacy transform (pd_common.cuh): a zero mean draws nothing, a mean
  * below 10 multiplies uniforms until the product drops to exp(-mean), PTRS above.
  *
- * Shape of one step (this is where the kernel differs from the reference's nested loops, without
- * changing which uniform goes to which event):
- *   1. RATE PASS, all lanes in lockstep: every event's mean and its code -- exp(-mean) for the
- *      multiplication method, -mean for PTRS -- go to shared memory [event][thread]; a bit mask
- *      remembers which events draw at all.
- *   2. DRAW LOOP, flattened: the lane walks its OWN live events while the warp walks the uniform
- *      stream together.  One trip = one Philox block = two uniforms for every lane; each uniform
- *      either continues the lane's current product or finishes its event (clamp, move, advance
- *      to the lane's next live event).  The trip count of a warp is the largest TOTAL number of
- *      uniforms any lane needs in the step, instead of the sum over events of the per-event
- *      maxima that the nested event-major loop pays.
- *   3. the live counts sit in shared memory [compartment][thread] (conflict-free whatever event a
- *      lane is at), so an event's source / destination may be a run-time index.
+ * The rates of a step are frozen at its start and a Poisson draw does not look at the counts, so
+ * only the clamp-and-move has to run in event order.  One step is therefore three passes, none
+ * of which changes which uniform goes to which event:
+ *   1. RATE PASS, all lanes in lockstep: every live event's code -- exp(-mean) for the
+ *      multiplication method, -mean for PTRS -- is appended to the lane's list in shared memory
+ *      [k][thread]; a bit mask remembers which flow-table rows are in the list.
+ *   2. DRAW LOOP, flattened: the lane walks its OWN list while the warp walks the uniform stream
+ *      together.  One trip = one Philox block = two uniforms for every lane; each uniform either
+ *      continues the lane's current product or ends its event, whose draw X then overwrites the
+ *      code in the list.  The trip count of a warp is the largest TOTAL number of uniforms any
+ *      lane needs in the step, instead of the sum over events of the per-event maxima that the
+ *      nested event-major loop pays.
+ *   3. APPLY PASS, lockstep again: the flow-table rows in order, compartment indices literal,
+ *      clamp to the current source count and move.
  */
 #include "pd_model.h"
 #include "pd_common.cuh"
@@ -36,30 +37,28 @@ struct PdTauLaunch {
 
 #if PD_TAU_NROW <= 32
 typedef pd_u32 pd_mask;
-#define PD_MASK_FIRST(x) (__ffs((int)(x)) - 1)
 #elif PD_TAU_NROW <= 64
 typedef pd_u64 pd_mask;
-#define PD_MASK_FIRST(x) (__ffsll((long long)(x)) - 1)
 #else
 #error "the tau-leap kernel handles at most 64 flow-table rows"
 #endif
 
-/* event table word: source | destination << 16, 0xffff = none (entry has no source, death no
- * destination); generated per model as PD_TAU_EVENT_TABLE over the rows that can fire */
-__device__ const pd_u32 pd_event_table[PD_TAU_NROW_DIM] = PD_TAU_EVENT_TABLE;
-
-/* ring slots: the live counts of target index `it` sit in slot it % PD_NSLOT */
-#if PD_OUT_MODE == PD_OUT_STATS
-#define PD_NSLOT PD_EPOCH
-#else
-#define PD_NSLOT 1
-#endif
-/* the kernel's dynamic shared memory, read by the host after loading the module
+/* the kernel's dynamic shared memory (the draw list), read by the host after loading the module
  * (csrc/popdyn_capi.cu) */
 extern "C" __device__ unsigned int pd_smem_bytes =
-    (unsigned int)(PD_CODE_SMEM_BYTES(PD_TAU_NROW, PD_BLOCK) +
-                   PD_RING_SMEM_BYTES(PD_NSLOT, PD_C, PD_BLOCK, sizeof(pd_count)) +
-                   PD_TAB_SMEM_BYTES(PD_TAU_NROW));
+    (unsigned int)PD_CODE_SMEM_BYTES(PD_TAU_NROW, PD_BLOCK);
+
+/* a finished draw is parked in the list cell of its code; with 32-bit counts it saturates at
+ * 2^31 - 1, which changes nothing: a clamp brings it down to a count anyway and an unclamped
+ * gain of that size raises PD_ERR_COUNT_RANGE either way */
+__device__ __forceinline__ void pd_park_draw(double *cell, pd_i64 k) {
+  if (sizeof(pd_count) == 4) *(int *)cell = (k > 0x7fffffffLL) ? 0x7fffffff : (int)k;
+  else *(pd_i64 *)cell = k;
+}
+__device__ __forceinline__ void pd_park_draw(double *cell, int x) {
+  if (sizeof(pd_count) == 4) *(int *)cell = x;
+  else *(pd_i64 *)cell = (pd_i64)x;
+}
 
 extern "C" __global__ void __launch_bounds__(PD_BLOCK, PD_MIN_BLOCKS)
 pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
@@ -71,49 +70,39 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   const pd_i64 M = a.n_member;
 
   extern __shared__ double s_dyn[];
-  double *s_code = s_dyn;                                          /* [PD_TAU_NROW][PD_BLOCK]   */
-  pd_count *s_ring = (pd_count *)((char *)s_dyn + PD_CODE_SMEM_BYTES(PD_TAU_NROW, PD_BLOCK));
-  pd_u32 *s_tab = (pd_u32 *)((char *)s_ring +
-                             PD_RING_SMEM_BYTES(PD_NSLOT, PD_C, PD_BLOCK, sizeof(pd_count)));
+  double *const s_list = s_dyn + tid;                       /* [k][PD_BLOCK], this lane's column */
 #if PD_OUT_MODE == PD_OUT_STATS
-  const pd_i64 block_member0 = (pd_i64)blockIdx.x * PD_BLOCK;
-  const int n_active = (M - block_member0 < PD_BLOCK) ? (int)(M - block_member0) : PD_BLOCK;
+  __shared__ PdStatsPart s_acc;
 #endif
-  for (int e = tid; e < PD_TAU_NROW_DIM; e += PD_BLOCK) s_tab[e] = pd_event_table[e];
-  __syncthreads();
 
+  pd_count y[PD_C];
   double pm[PD_NPM_DIM];
   PdRng rng;
   pm[0] = 0.0;
-  pd_count *s_y = s_ring;                                   /* slot of target index 0 */
   if (active) {
 #pragma unroll
     for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * M + m];
 #pragma unroll
     for (int c = 0; c < PD_C; ++c) {
       const double v = pd_load_y0(a.y0, a.y0_stride_c, a.y0_stride_m, c, m);
-      s_y[c * PD_BLOCK + tid] = (pd_count)v;                /* int() truncation, :805-806 */
+      y[c] = (pd_count)v;                                   /* int() truncation, :805-806 */
 #if PD_OUT_MODE == PD_OUT_FULL
       a.soln[(size_t)c * M + m] = v;                        /* row 0 = untruncated y, :813 */
 #endif
     }
     rng.init(a, m);
+  } else {
+#pragma unroll
+    for (int c = 0; c < PD_C; ++c) y[c] = 0;
   }
 #if PD_OUT_MODE == PD_OUT_STATS
-  if (a.n_time == 1) pd_stats_flush(a, s_ring, 0, 1, n_active, a.member0 + block_member0);
+  pd_stats_step(a, s_acc, y, active, 0, 0, a.member0 + m);
+  if (PD_EPOCH == 1 || a.n_time == 1) pd_stats_part_flush(a, s_acc, 0, 1);
 #endif
 
   int bad = 0;
   double time = a.target[0];
   for (int it = 1; it < a.n_time; ++it) {
-#if PD_NSLOT > 1
-    const int slot = it % PD_NSLOT;
-    const pd_count *s_prev = s_ring + ((slot ? slot : PD_NSLOT) - 1) * (PD_C * PD_BLOCK);
-    s_y = s_ring + slot * (PD_C * PD_BLOCK);
-#else
-    const int slot = 0;
-    const pd_count *s_prev = s_ring;
-#endif
     if (active) {
       const double dt = a.target[it] - a.target[it - 1];    /* :820 */
 
@@ -121,20 +110,16 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
        * is formed from them, the live counts only enter through the clamps (:833-841) */
       double yd[PD_C], mult[PD_NMULT_DIM];
 #pragma unroll
-      for (int c = 0; c < PD_C; ++c) {
-        const pd_count have = s_prev[c * PD_BLOCK + tid];
-#if PD_NSLOT > 1
-        s_y[c * PD_BLOCK + tid] = have;                     /* this step's slot starts as a copy */
-#endif
-        yd[c] = (double)have;
-      }
+      for (int c = 0; c < PD_C; ++c) yd[c] = (double)y[c];
       pd_event_mults(yd, U, pm, time, (const double *)0, mult);
       pd_mask live = 0;
+      int end = 0;                                          /* append cursor (list offset) */
 #define PD_TAU_CODE(e, mean)                                                         \
   if (mean > 0.0) {                                                                  \
     double code;                                                                     \
     if (mean >= 10.0) code = -mean; else code = pd_exp_nonpos(-mean);                \
-    s_code[e * PD_BLOCK + tid] = code;                                               \
+    s_list[end] = code;                                                              \
+    end += PD_BLOCK;                                                                 \
     live |= (pd_mask)1 << e;                                                         \
   } else if (!(mean == 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }
 #define PD_TAU_ENTRY(e, to, is_int, rate)                                            \
@@ -149,72 +134,26 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #undef PD_TAU_DEATH
 #undef PD_TAU_CODE
 
-      /* ---- 2. draw loop.  Lane state: remaining live events (lowest bit = current event e),
-       * the current event's code, running product and count */
-      int e = live ? PD_MASK_FIRST(live) : 0;
-      double code = s_code[e * PD_BLOCK + tid];
+      /* ---- 2. draw loop.  Lane state: list cursor, the current event's code, its running
+       * product and count */
+      int cur = 0;
+      double code = s_list[0];
       double prod = 1.0;
       int X = 0;
-
-/* step to the lane's next live event */
-#define PD_TAU_ADVANCE                                                               \
-  live &= live - 1;                                                                  \
-  if (live) {                                                                        \
-    e = PD_MASK_FIRST(live);                                                         \
-    code = s_code[e * PD_BLOCK + tid];                                               \
-    prod = 1.0; X = 0;                                                               \
-  }
-/* finish the current event with the draw X of the multiplication method: clamp to the CURRENT
- * source count (:833-834, :839-840), move, births unclamped (:842-844).  With 32-bit counts a
- * gain that would pass 2^31 - 1 raises the error flag instead of wrapping (numpy / Python ints
- * never wrap): both terms are non-negative, so the unsigned sum cannot wrap itself */
-#define PD_TAU_FINISH_SMALL                                                          \
+/* the current event ends with draw d: park it, step to the lane's next event */
+#define PD_TAU_NEXT(d)                                                               \
   {                                                                                  \
-    const pd_u32 ft = s_tab[e];                                                      \
-    const int from = (int)(ft & 0xffffu), to = (int)(ft >> 16);                      \
-    pd_count d = (pd_count)X;                                                        \
-    if (from != 0xffff) {                                                            \
-      const pd_count have = s_y[from * PD_BLOCK + tid];                              \
-      d = d < have ? d : have;                                                       \
-      s_y[from * PD_BLOCK + tid] = have - d;                                         \
-    }                                                                                \
-    if (to != 0xffff) {                                                              \
-      const pd_count have = s_y[to * PD_BLOCK + tid];                                \
-      if (sizeof(pd_count) == 4) {                                                   \
-        const pd_u32 sum = (pd_u32)have + (pd_u32)d;                                 \
-        if (sum > 0x7fffffffu) { if (!bad) bad = PD_ERR_COUNT_RANGE; }               \
-        else s_y[to * PD_BLOCK + tid] = (pd_count)sum;                               \
-      } else s_y[to * PD_BLOCK + tid] = have + d;                                    \
-    }                                                                                \
-    PD_TAU_ADVANCE                                                                   \
-  }
-/* the same after PTRS, whose draw may exceed 32 bits */
-#define PD_TAU_FINISH_BIG(k_in)                                                      \
-  {                                                                                  \
-    pd_i64 d = (k_in);                                                               \
-    const pd_u32 ft = s_tab[e];                                                      \
-    const int from = (int)(ft & 0xffffu), to = (int)(ft >> 16);                      \
-    if (from != 0xffff) {                                                            \
-      const pd_count have = s_y[from * PD_BLOCK + tid];                              \
-      if (d > (pd_i64)have) d = (pd_i64)have;                                        \
-      s_y[from * PD_BLOCK + tid] = have - (pd_count)d;                               \
-    }                                                                                \
-    if (to != 0xffff) {                                                              \
-      const pd_count have = s_y[to * PD_BLOCK + tid];                                \
-      if (sizeof(pd_count) == 4 && (pd_i64)have + d > 0x7fffffffLL) {                \
-        if (!bad) bad = PD_ERR_COUNT_RANGE;                                          \
-      } else s_y[to * PD_BLOCK + tid] = have + (pd_count)d;                          \
-    }                                                                                \
-    PD_TAU_ADVANCE                                                                   \
+    pd_park_draw(&s_list[cur], d);                                                   \
+    cur += PD_BLOCK;                                                                 \
+    if (cur != end) { code = s_list[cur]; prod = 1.0; X = 0; }                       \
   }
 /* one uniform of the multiplication method */
 #define PD_TAU_MULT(u)                                                               \
   {                                                                                  \
     prod *= (u);                                                                     \
-    if (prod > code) X += 1; else PD_TAU_FINISH_SMALL                                \
+    if (prod > code) X += 1; else PD_TAU_NEXT(X)                                     \
   }
-
-      while (live) {
+      while (cur != end) {
         if (code < 0.0) {
           /* PTRS event (mean >= 10): one attempt = the next two uniforms of the same stream,
            * judged out of line; the lane rejoins the block-wise walk at the next trip */
@@ -232,7 +171,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
           if (rng.exhausted) break;
 #endif
           const pd_i64 k = pd_poisson_ptrs_attempt(-code, u, v);
-          if (k >= 0) PD_TAU_FINISH_BIG(k)
+          if (k >= 0) PD_TAU_NEXT(k)
           continue;
         }
 #if PD_RNG_MODE == PD_RNG_PHILOX
@@ -242,7 +181,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
           rng.has_spare = 1;
           PD_TAU_MULT(u0)
         }
-        if (live && code >= 0.0) {          /* the block's second uniform, or the pending spare */
+        if (cur != end && code >= 0.0) {    /* the block's second uniform, or the pending spare */
           rng.has_spare = 0;
           PD_TAU_MULT(rng.spare)
         }
@@ -253,27 +192,59 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #endif
       }
 #undef PD_TAU_MULT
-#undef PD_TAU_FINISH_SMALL
-#undef PD_TAU_FINISH_BIG
-#undef PD_TAU_ADVANCE
+#undef PD_TAU_NEXT
+
+      /* ---- 3. apply pass, flow-table order: clamp to the CURRENT source count (:833-834,
+       * :839-840), move; births unclamped (:842-844).  Branch-free: a row that is not in the
+       * list takes d = 0.  With 32-bit counts a gain that passes 2^31 - 1 sets the sign bit at
+       * that moment (both terms are non-negative, the sum cannot wrap past it); the OR of every
+       * updated count is checked once per step and raises the error flag (numpy / Python ints
+       * never wrap). */
+      if (!rng.exhausted) {
+        int get = 0;
+        pd_count signs = 0;
+#define PD_TAU_TAKE(e, d)                                                            \
+  const bool on_##e = (live >> e) & 1;                                               \
+  pd_count d = 0;                                                                    \
+  if (on_##e) d = (sizeof(pd_count) == 4) ? (pd_count)*(const int *)&s_list[get]     \
+                                          : (pd_count)*(const pd_i64 *)&s_list[get]; \
+  get += on_##e ? PD_BLOCK : 0;
+#define PD_TAU_ENTRY(e, to, is_int, rate)                                            \
+  { PD_TAU_TAKE(e, d) y[to] += d; signs |= y[to]; }
+#define PD_TAU_TRANSFER(e, from, to, rate)                                           \
+  { PD_TAU_TAKE(e, d) d = d < y[from] ? d : y[from]; y[from] -= d; y[to] += d; signs |= y[to]; }
+#define PD_TAU_DEATH(e, from, rate)                                                  \
+  { PD_TAU_TAKE(e, d) d = d < y[from] ? d : y[from]; y[from] -= d; }
+        PD_FOR_EACH_TAU_ROW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
+#undef PD_TAU_ENTRY
+#undef PD_TAU_TRANSFER
+#undef PD_TAU_DEATH
+#undef PD_TAU_TAKE
+        if (sizeof(pd_count) == 4 && signs < 0 && !bad) bad = PD_ERR_COUNT_RANGE;
+      }
       time += dt;                                           /* :848 */
 #if PD_OUT_MODE == PD_OUT_FULL
 #pragma unroll
       for (int c = 0; c < PD_C; ++c)
-        a.soln[((size_t)it * PD_C + c) * M + m] = (double)s_y[c * PD_BLOCK + tid];   /* :850-852 */
+        a.soln[((size_t)it * PD_C + c) * M + m] = (double)y[c];   /* :850-852 */
 #endif
     }
 #if PD_OUT_MODE == PD_OUT_STATS
-    /* end of an epoch: the block reduces the ring (two barriers inside) */
-    if (slot == PD_NSLOT - 1 || it == a.n_time - 1)   /* block-uniform */
-      pd_stats_flush(a, s_ring, it - slot, slot + 1, n_active, a.member0 + block_member0);
+    {
+      /* the warp records this target time; at the end of an epoch the block moves its
+       * accumulators to global memory (two barriers inside pd_stats_part_flush) */
+      const int slot = it % PD_EPOCH;
+      pd_stats_step(a, s_acc, y, active, it, slot, a.member0 + m);
+      if (slot == PD_EPOCH - 1 || it == a.n_time - 1)       /* block-uniform */
+        pd_stats_part_flush(a, s_acc, it - slot, slot + 1);
+    }
 #endif
   }
 
   if (active) {
 #if PD_OUT_MODE == PD_OUT_FINAL
 #pragma unroll
-    for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * M + m] = (double)s_y[c * PD_BLOCK + tid];
+    for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * M + m] = (double)y[c];
 #endif
     if (!bad && rng.exhausted) bad = PD_ERR_STREAM;
     if (bad) pd_raise(a.err, bad, a.member0 + m, 0);
