@@ -35,14 +35,14 @@ QUANTILES = [0.025, 0.25, 0.5, 0.75, 0.975]
 HIST_BINS = 2048
 HIST_MAX = 2047          # strains counts stay well below 2048 (S ~ 1000-2000): width-1 bins
 # Roofline unit costs of pd_tau_leap_kernel on this workload (measured with
-# ncu, profiles/r1_tau_leap_stats_ncu_summary.txt): the kernel is bound by SM instruction issue,
+# ncu, profiles/r1_tau_leap_stats_bench_ncu_summary.txt): the kernel is bound by SM instruction issue,
 # so the work unit is the thread-instruction.
 #   USEFUL_INST_PER_MEMBER_STEP: predicated-on thread instructions one member-step needs
 #   (smsp__thread_inst_executed_pred_on.sum / member-steps of the captured launch);
 #   HBM bytes per member-step: the streaming-statistics mode reads y0 once and writes nothing per
 #   step; DRAM_BYTES_PER_MEMBER_STEP is dram__bytes_read+write of the same capture per member-step.
-USEFUL_INST_PER_MEMBER_STEP = 1350.0
-DRAM_BYTES_PER_MEMBER_STEP = None
+USEFUL_INST_PER_MEMBER_STEP = 1332.0   # thread_inst_executed_true 2.6635e12 / 2e9 member-steps
+DRAM_BYTES_PER_MEMBER_STEP = 0.0042    # dram__bytes_read 8.37 MB + write 512 B over 2e9 member-steps
 SM_COUNT = 148
 LANES_PER_SM_PER_CLK = 128          # 4 schedulers x 1 warp instruction x 32 lanes
 
@@ -375,7 +375,7 @@ def main():
     ap.add_argument('--members', type=int, default=10**7, help='members per GPU')
     ap.add_argument('--count-bits', type=int, default=32, choices=[32, 64],
                     help='width of the integer counts (32: overflow raises the device error flag)')
-    ap.add_argument('--min-blocks', type=int, default=3, help='__launch_bounds__ resident-block cap')
+    ap.add_argument('--min-blocks', type=int, default=4, help='__launch_bounds__ resident-block cap')
     ap.add_argument('--block', type=int, default=256)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     args = ap.parse_args()
