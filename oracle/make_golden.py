@@ -111,6 +111,18 @@ def main():
     m.make_times(0, 120, 1); m.integrate('discrete_time_stochastic')
     out['seird_dts_seed5'] = m.soln_array
 
+    # ---- scale-up functions inside the stochastic loops (declared extension):
+    # the reference class with calculate_vars calling calculate_scaleup_vars() first
+    class ScaleupTb(tb):
+        def calculate_vars(self):
+            self.calculate_scaleup_vars()
+            tb.calculate_vars(self)
+    for method, tag, times in (('discrete_time_stochastic', 'dts', (1985, 2000, 1.)),
+                               ('continuous_time_stochastic', 'cts', (1988, 1992, 1.))):
+        reference.seed_all(9)
+        m = ScaleupTb([]); m.make_times(*times); m.integrate(method)
+        out['tb_scaleup_%s_seed9' % tag] = m.soln_array
+
     # ---- injected-stream runs ------------------------------------------------------------
     for k in range(4):
         u = injected_stream(100 + k, 20000)

@@ -291,6 +291,7 @@ void pdo_eval_vars(const pdo_model *m, const double *y, const double *params, do
     case PDO_OP_NOT: r = !(a != 0.0); break;
     case PDO_OP_ISFINITE: r = isfinite(a) ? 1.0 : 0.0; break;
     case PDO_OP_SELECT: r = (a != 0.0) ? b : c; break;
+    case PDO_OP_EXP: r = exp(a); break;
     default: r = NAN;
     }
     v[base + k] = r;

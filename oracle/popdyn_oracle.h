@@ -31,7 +31,8 @@ enum {
   PDO_OP_LT, PDO_OP_LE, PDO_OP_GT, PDO_OP_GE, PDO_OP_EQ, PDO_OP_NE, /* -> 0.0 / 1.0        */
   PDO_OP_AND, PDO_OP_OR, PDO_OP_NOT,
   PDO_OP_ISFINITE,
-  PDO_OP_SELECT /* a ? b : c                                                               */
+  PDO_OP_SELECT, /* a ? b : c                                                              */
+  PDO_OP_EXP     /* libm exp: scale-up curves, basepop.py:122                              */
 };
 
 /* flow kinds in the canonical evaluation order, basepop.py:566-598 / :703-735 */

@@ -34,7 +34,7 @@ KIND_NAMES = ('entry', 'var', 'fixed', 'bgdeath', 'infdeath')
 
 # opcode numbering shared with oracle/popdyn_oracle.h
 OPS = ('const', 'add', 'sub', 'mul', 'div', 'neg', 'fabs', 'floor', 'lt', 'le', 'gt', 'ge',
-       'eq', 'ne', 'and', 'or', 'not', 'isfinite', 'select')
+       'eq', 'ne', 'and', 'or', 'not', 'isfinite', 'select', 'exp')
 OPCODE = {name: i for i, name in enumerate(OPS)}
 _BOOL_OPS = frozenset(('lt', 'le', 'gt', 'ge', 'eq', 'ne', 'and', 'or', 'not', 'isfinite'))
 
@@ -57,6 +57,7 @@ class Graph(object):
         self.const_values = {}
         self.assertions = []   # node ids recorded by traced `assert` statements
         self.collect_asserts = False
+        self.explorer = None   # _BranchExplorer while a scale-up closure is being traced
 
     def add(self, op, a=-1, b=-1, c=-1):
         key = (op, a, b, c)
@@ -166,6 +167,10 @@ class Sym(object):
 
     # -- loud rejections --------------------------------------------------------------------
     def __bool__(self):
+        if self.g.explorer is not None and self.is_bool:
+            # inside a scale-up closure: Python branches on the traced time are explored path
+            # by path and joined with selects (_trace_scalar_function)
+            return self.g.explorer.decide(self.n)
         if self.g.collect_asserts:
             # inside a traced checks(): `assert cond` becomes a device-side assertion
             self.g.assertions.append(self.n)
@@ -264,6 +269,85 @@ def traced_sum(iterable, start=0, naive=False):
         cond = g.add('and', nonzero, finite)
         total = Sym(g, g.add('select', cond, (total + comp).n, total.n))
     return total
+
+
+class _BranchExplorer(object):
+    """Decision record of one run of a scale-up closure: the first ``len(forced)`` traced
+    comparisons take the forced outcomes, later ones take True and are recorded."""
+
+    def __init__(self, forced):
+        self.forced = list(forced)
+        self.taken = []          # (cond node, outcome) of every comparison met, in order
+
+    def decide(self, node):
+        k = len(self.taken)
+        outcome = self.forced[k] if k < len(self.forced) else True
+        self.taken.append((node, outcome))
+        return outcome
+
+
+def traced_exp(x):
+    """``math.exp`` while a hook is traced: an 'exp' node for a traced value."""
+    if isinstance(x, Sym):
+        if x.is_bool:
+            raise TraceError('exp() of a traced comparison result')
+        return Sym(x.g, x.g.add('exp', x.n))
+    return _real_exp(x)
+
+
+_real_exp = math.exp
+
+
+@contextlib.contextmanager
+def _patched_exp():
+    """Scale-up closures call ``math.exp`` (basepop.py:122): while one is traced, the stdlib
+    function is shadowed by a version that records an 'exp' node for traced arguments."""
+    math.exp = traced_exp
+    try:
+        yield
+    finally:
+        math.exp = _real_exp
+
+
+def _trace_scalar_function(g, fn, x, what, max_paths=64):
+    """Trace ``fn(x)`` for a traced scalar ``x`` where ``fn`` may branch on comparisons of ``x``
+    (basepop.py:120-121 `if arg > 10.`, :148-155, examples/tb_model.py:93): every path is run
+    once with its branch outcomes forced and the results are joined by selects on the recorded
+    conditions.  ``fn`` must be a pure function of ``x``."""
+    runs = [0]
+
+    def run(forced):
+        runs[0] += 1
+        if runs[0] > max_paths:
+            raise TraceError('%s branches into more than %d paths' % (what, max_paths))
+        explorer = _BranchExplorer(forced)
+        previous, g.explorer = g.explorer, explorer
+        try:
+            with _patched_exp():
+                value = fn(x)
+        finally:
+            g.explorer = previous
+        if isinstance(value, Sym):
+            if value.is_bool:
+                raise TraceError('%s returns a comparison result, not a number' % what)
+        elif isinstance(value, numbers.Real):
+            value = Sym(g, g.const(float(value)))
+        else:
+            raise TraceError('%s returned %s, not a number' % (what, type(value).__name__))
+        return value, explorer.taken
+
+    def build(forced):
+        value, taken = run(forced)
+        if len(taken) <= len(forced):
+            return value
+        # the first unforced comparison: this run took True there
+        cond = taken[len(forced)][0]
+        outcomes = [o for _, o in taken[:len(forced)]]
+        if_true = build(outcomes + [True])
+        if_false = build(outcomes + [False])
+        return Sym(g, g.add('select', cond, if_true.n, if_false.n))
+
+    return build([])
 
 
 def _fold0(total, x):
@@ -478,6 +562,14 @@ def compile_model(model, method, is_continue=False, naive_sum=None):
         # :822-824): whatever is left in self.vars is visible as stale constants
         traced_vars = {k: v for k, v in model.vars.items() if isinstance(v, numbers.Real)}
 
+    def traced_scaleup_vars():
+        # a hook that calls self.calculate_scaleup_vars() itself (declared extension for the
+        # stochastic integrators): the closures are traced on the symbolic time
+        # and evaluated on the device at every member's own time
+        for label, fn in model.scaleup_fns.items():
+            model.vars[label] = _trace_scalar_function(g, fn, time_sym,
+                                                       'scale-up function %r' % (label,))
+
     # flow lists whose resolved rates are parameter symbols while the hooks run
     fixed_syms = []
     for from_label, to_label, rate in model.fixed_transfer_rate_flows:
@@ -517,8 +609,13 @@ def compile_model(model, method, is_continue=False, naive_sum=None):
         model.infection_death_rate_flows = inf_syms
         if bg_sym is not None:
             model.background_death_rate = bg_sym
-        with _patched_sum(naive_sum):
-            model.calculate_vars()
+        if method != 'explicit':
+            model.calculate_scaleup_vars = traced_scaleup_vars
+        try:
+            with _patched_sum(naive_sum):
+                model.calculate_vars()
+        finally:
+            model.__dict__.pop('calculate_scaleup_vars', None)
         hook_vars = dict(model.vars)
 
         def as_sym(value, what):

@@ -25,6 +25,8 @@ def make_model(name, **kw):
         m = models.SimpleTbModel([])
     elif name == 'tb_vacc':
         m = models.SimpleTbModel(['vaccination'])
+    elif name == 'tb_scaleup':
+        m = models.ScaleupTbModel(kw.get('interventions', []))
     elif name == 'rmit':
         m = models.RmitTbModel(dict(RMIT, **kw.get('params', {'beta': 50.})))
     else:

@@ -165,6 +165,29 @@ def test_injected_stream_bit_exact_reaches_ptrs_branch():
     _inject('discrete_time_stochastic', 'seird', 64, 20000, (0, 60, 1), seed=7, params=params)
 
 
+@pytest.mark.parametrize('method,times,n_uniform', [
+    ('discrete_time_stochastic', (1985, 2000, 1.), 4000),
+    ('continuous_time_stochastic', (1988, 1988.02, .01), 8000),
+])
+def test_injected_stream_bit_exact_tb_with_device_scaleups(method, times, n_uniform):
+    # BASELINE config 4: sigmoidal scale-up closures traced (branches explored, math.exp lowered)
+    # and evaluated on the device at every member's own time; population 1e6 -> every Poisson
+    # mean is in the PTRS branch
+    _inject(method, 'tb_scaleup', 40, n_uniform, times, seed=8)
+
+
+def test_native_philox_tb_with_device_scaleups_matches_oracle():
+    m = helpers.make_model('tb_scaleup')
+    m.make_times(1985, 1995, 1.)
+    n, seed = 70, 4
+    res = m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='full', seed=seed)
+    om = oracle.OracleModel(helpers.compiled(m, 'discrete_time_stochastic'))
+    for i in (0, 1, 37, 69):
+        want, _, err = om.tau_leap(m.get_init_list(), m.target_times,
+                                   oracle.Rng('philox', seed=seed, member=i))
+        assert err == 0 and np.array_equal(res.soln[:, :, i], want)
+
+
 def test_injected_stream_golden_runs_of_the_reference(golden):
     for tag, method, base in (('dts', 'discrete_time_stochastic', 100),
                               ('cts', 'continuous_time_stochastic', 200)):

@@ -110,6 +110,21 @@ def test_seeded_runs_reaching_the_ptrs_branch(golden):
     assert_bitwise(soln, golden['seird_dts_seed5'])
 
 
+@pytest.mark.parametrize('method,tag,kind,times', [
+    ('discrete_time_stochastic', 'dts', 'numpy', (1985, 2000, 1.)),
+    ('continuous_time_stochastic', 'cts', 'python', (1988, 1992, 1.)),
+])
+def test_scaleup_functions_inside_the_stochastic_loops(golden, method, tag, kind, times):
+    # BASELINE config 4: the reference's TB class with calculate_vars calling
+    # calculate_scaleup_vars() first; its sigmoidal closures branch on time and call math.exp,
+    # the tracer explores the branches and the oracle evaluates them at every member's own time
+    m = helpers.make_model('tb_scaleup')
+    m.make_times(*times)
+    soln, _, err = helpers.oracle_stochastic(m, method, oracle.Rng(kind, 9))
+    assert err == 0
+    assert_bitwise(soln, golden['tb_scaleup_%s_seed9' % tag])
+
+
 @pytest.mark.parametrize('k', range(4))
 def test_injected_stream_runs(golden, k):
     for tag, method, seed in (('dts', 'discrete_time_stochastic', 100 + k),

@@ -76,6 +76,29 @@ def test_tb_model_fails_the_same_way_under_stochastic_methods():
         compiler.compile_model(ours, 'discrete_time_stochastic')
 
 
+@pytest.mark.parametrize('method,kind,times', [
+    ('discrete_time_stochastic', 'numpy', (1960, 1975, 1.)),
+    ('continuous_time_stochastic', 'python', (1969, 1971, 1.)),
+])
+def test_tb_with_scaleups_in_the_stochastic_loops_matches_the_reference(method, kind, times):
+    # the declared extension for config 4: same subclass on both sides
+    base = reference.example_classes('tb_model.py')['SimpleTbModel']
+
+    class Theirs(base):
+        def calculate_vars(self):
+            self.calculate_scaleup_vars()
+            base.calculate_vars(self)
+
+    reference.seed_all(21)
+    theirs = Theirs(['vaccination'])
+    theirs.make_times(*times)
+    theirs.integrate(method)
+    ours = helpers.make_model('tb_scaleup', interventions=['vaccination'])
+    ours.make_times(*times)
+    soln, _, err = helpers.oracle_stochastic(ours, method, oracle.Rng(kind, 21))
+    assert err == 0 and np.array_equal(soln, theirs.soln_array)
+
+
 def test_golden_file_is_current(golden):
     # the committed fixtures are what the reference produces today
     m = reference.example_classes('sir_model.py')['SirModel']()

@@ -1,3 +1,2 @@
-python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; tail -c 2500 gpurun_out/bench_r1.json; tail -3 gpurun_out/bench_r1.err
-ncu --set full --import-source on --clock-control none -k pd_tau_leap_kernel -c 1 -o gpurun_out/tau_stats_bench_r1 python bench.py --steps 1 --warmup 0 --cpu-seconds 1 --members 2000000 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log | cut -c1-200
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 1 --cpu-seconds 1 > gpurun_out/ncu_launch.log 2>&1; tail -1 gpurun_out/ncu_launch.log | cut -c1-200
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -8 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
