@@ -178,9 +178,12 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
                  member_offset=0, uniforms=None, device=0, count_bits=64, block=256,
                  hist_bins=0, hist_max=None, hist_times=None, out=None, moments=None,
                  hist=None, member_params=None, y0=None, stream=None, min_dt=None,
-                 min_blocks=0):
+                 min_blocks=0, statistics='host'):
     """Launch one compiled model.  Returns an EnsembleResult.  ``out`` / ``moments`` / ``hist`` /
-    ``member_params`` / ``y0`` let the caller supply resident (torch CUDA) buffers."""
+    ``member_params`` / ``y0`` let the caller supply resident (torch CUDA) buffers.
+    ``statistics='device'`` keeps the streaming-statistics accumulators (moments, histograms)
+    in HBM as torch tensors created here: only what ``mean`` / ``var`` / ``quantiles`` return
+    ever crosses PCIe, not the histograms themselves."""
     method_code = capi.METHOD_CODES[method]
     out_code = capi.OUTPUT_CODES[output]
     rng_code = capi.INJECT if uniforms is not None else capi.PHILOX
@@ -252,15 +255,30 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
     else:
         if method == 'explicit':
             raise ValueError("output='stats' is defined for the stochastic integrators")
-        res.moments = moments if moments is not None else numpy.zeros((T, C, 2), numpy.uint64)
+        on_device = statistics == 'device'
+        if statistics not in ('host', 'device'):
+            raise ValueError("statistics must be 'host' or 'device'")
+        if on_device:
+            import torch
+            cuda = torch.device('cuda', device)
+        if moments is not None:
+            res.moments = moments
+        elif on_device:
+            res.moments = torch.zeros((T, C, 2), dtype=torch.int64, device=cuda)
+        else:
+            res.moments = numpy.zeros((T, C, 2), numpy.uint64)
         run.moments = capi.address(res.moments)
         if hist_bins:
             if hist_max is None:
                 raise ValueError('hist_max (largest expected count per compartment) is needed '
                                  'with hist_bins; see ensemble.pilot_hist_max')
             row, shift, rows = _hist_setup(T, C, hist_bins, hist_max, hist_times)
-            res.hist = hist if hist is not None else numpy.zeros((len(rows), C, hist_bins),
-                                                                 numpy.uint32)
+            if hist is not None:
+                res.hist = hist
+            elif on_device:
+                res.hist = torch.zeros((len(rows), C, hist_bins), dtype=torch.int32, device=cuda)
+            else:
+                res.hist = numpy.zeros((len(rows), C, hist_bins), numpy.uint32)
             res.hist_times, res.hist_shift, res.hist_bins = rows, shift, hist_bins
             keep += [row, shift]
             run.hist, run.hist_row = capi.address(res.hist), capi.address(row)
@@ -308,7 +326,7 @@ def integrate_single(model, y, method, is_continue):
 def integrate_ensemble(model, method='explicit', n_members=None, output='full', seed=0,
                        member_offset=0, uniforms=None, device=None, count_bits=64, block=256,
                        hist_bins=0, hist_max=None, hist_times=None, check=True, min_blocks=0,
-                       **buffers):
+                       statistics='host', **buffers):
     """
     Run ``n_members`` independent members of ``model`` (additive API, see module docstring).
 
@@ -341,7 +359,7 @@ def integrate_ensemble(model, method='explicit', n_members=None, output='full', 
                        seed=seed, member_offset=member_offset, uniforms=uniforms, device=device,
                        count_bits=count_bits, block=block, hist_bins=hist_bins,
                        hist_max=hist_max, hist_times=hist_times, min_blocks=min_blocks,
-                       **buffers)
+                       statistics=statistics, **buffers)
     if check:
         raise_device_error(res.info, method)
     return res

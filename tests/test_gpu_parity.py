@@ -331,6 +331,21 @@ def test_statistics_large_counts_binned_and_subset_of_times():
             assert np.array_equal(stats.hist[r, c], want)
 
 
+def test_statistics_kept_on_the_device_equal_host_statistics():
+    q = [0.025, 0.5, 0.975]
+    kw = dict(n_members=3000, output='stats', seed=12, hist_bins=2048, hist_max=2047)
+    m = helpers.make_model('strains')
+    m.make_times(0, 60, 1)
+    host = m.integrate_ensemble('discrete_time_stochastic', **kw)
+    dev = m.integrate_ensemble('discrete_time_stochastic', statistics='device', **kw)
+    assert hasattr(dev.hist, 'data_ptr') and dev.hist.is_cuda and dev.moments.is_cuda
+    assert dev.info['d2h_bytes'] < 4096          # no histogram crossed PCIe
+    assert np.array_equal(dev.moments.cpu().numpy().view(np.uint64), host.moments)
+    assert np.array_equal(dev.hist.cpu().numpy().view(np.uint32), host.hist)
+    assert np.array_equal(dev.quantiles(q).cpu().numpy(), host.quantiles(q))
+    assert np.array_equal(dev.mean(), host.mean()) and np.array_equal(dev.var(), host.var())
+
+
 def test_resident_torch_buffers_are_used_in_place():
     import torch
     m = helpers.make_model('strains')
