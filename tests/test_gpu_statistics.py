@@ -79,3 +79,41 @@ def test_explicit_ensemble_of_identical_members_is_identical(golden):
     n = 100000
     final = m.integrate_ensemble('explicit', n_members=n, output='final').final
     assert np.all(final == golden['seir_measles_explicit'][-1][:, None])
+
+
+def test_headline_configuration_at_full_size_through_size_independent_properties():
+    # BASELINE config 3 as bench.py runs it: 10^7 members x 1000 tau-leap steps, statistics on
+    # the device.  The oracle cannot run this size; what must hold at any size:
+    #   every member is recorded exactly once at every (t, c);
+    #   the first moment equals the histogram's own first moment (bin width 1, no overflow);
+    #   the second moment likewise;
+    #   two half-ensembles keyed by global member id add up to the whole, bit for bit.
+    import torch
+    m = helpers.make_model('strains')
+    m.make_times(0, 1000, 1)
+    n, bins = 10 ** 7, 2048
+    kw = dict(output='stats', seed=5, hist_bins=bins, hist_max=bins - 1, statistics='device',
+              count_bits=32)
+    whole = m.integrate_ensemble('discrete_time_stochastic', n_members=n, **kw)
+    hist = whole.hist.to(torch.int64)                               # [T][C][bins]
+    assert bool((hist.sum(dim=2) == n).all())
+    assert int(hist[..., bins - 1].sum()) == 0                      # nothing in the overflow bin
+    values = torch.arange(bins, device=hist.device, dtype=torch.int64)
+    assert torch.equal((hist * values).sum(dim=2), whole.moments[..., 0])
+    assert torch.equal((hist * values * values).sum(dim=2), whole.moments[..., 1])
+    half = n // 2
+    a = m.integrate_ensemble('discrete_time_stochastic', n_members=half, **kw)
+    b = m.integrate_ensemble('discrete_time_stochastic', n_members=n - half, member_offset=half,
+                             **kw)
+    assert torch.equal(a.moments + b.moments, whole.moments)
+    assert torch.equal(a.hist + b.hist, whole.hist)
+    # the reference's analytic pin at this size: P(invader extinct) -> 2/3 (dt = 1 bias < 0.02)
+    extinct = float(hist[-1, 2, 0]) / n
+    assert abs(extinct - 2. / 3.) < 0.02
+    # the mean total population obeys E[N'] = E[N] + 2 - 0.001 E[N] exactly (Poisson means are
+    # linear in the counts, clamps never bind for the deaths): N_t = 2000 - 909 * 0.999^t
+    for t in (1, 10, 100, 1000):
+        population = float(whole.moments[t, :, 0].sum()) / n
+        expected = 2000. - (2000. - 1091.) * 0.999 ** t
+        sigma = np.sqrt(2. * t + 1091.) / np.sqrt(n)               # generous bound on the s.e.
+        assert abs(population - expected) < 6 * sigma + 1e-6, (t, population, expected)
