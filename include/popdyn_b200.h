@@ -38,7 +38,8 @@ typedef enum {
 /* integrator selector: which reference loop the compiled kernel replaces */
 enum { PD_EXPLICIT = 0,   /* integrate_explicit,                      basepop.py:658-688      */
        PD_TAU_LEAP = 1,   /* integrate_discrete_time_stochastic,      basepop.py:797-852      */
-       PD_GILLESPIE = 2 };/* integrate_continuous_time_stochastic,    basepop.py:737-795      */
+       PD_GILLESPIE = 2,  /* integrate_continuous_time_stochastic,    basepop.py:737-795      */
+       PD_DIAGNOSTICS = 3 };/* calculate_diagnostics over stored times, basepop.py:911-960    */
 /* output selector */
 enum { PD_FULL = 0,       /* soln [T][C][M] fp64 (the reference's soln_array per member)      */
        PD_FINAL = 1,      /* final state [C][M] fp64                                          */
@@ -108,12 +109,27 @@ typedef struct {
   void *stream;
 } pd_explicit_run;
 
+/* The diagnostics pass over stored trajectories (model built with method PD_DIAGNOSTICS, the
+ * header generated from compile_model(..., diagnostics=True)).                                */
+typedef struct {
+  int64_t n_member;
+  int32_t n_time, n_var;          /* n_var must match the model header (PD_NDIAG)              */
+  const double *soln;             /* [T][C][M]: PD_FULL output, or [1][C][M] = a PD_FINAL one  */
+  const double *uniform_params;   /* [n_param] HOST                                            */
+  const double *member_params;    /* [n_member_param][M]                                       */
+  const double *times;            /* [T] HOST                                                  */
+  const double *scaleup_row;      /* [n_scaleup] HOST or NULL (explicit: last derivative call) */
+  double *var_soln;               /* [T][n_var][M]                                             */
+  double *flow_soln;              /* [T][C][M] or NULL                                         */
+  void *stream;
+} pd_diag_run;
+
 /* ---- library ---------------------------------------------------------------------------- */
 int pd_version(void);
 const char *pd_last_error(void);
 int pd_device_count(void);
 /* sizeof() of the ABI structs as compiled: 0 pd_model_desc, 1 pd_run_result, 2 pd_stoch_run,
- * 3 pd_explicit_run -- lets a foreign-language binding verify its struct layout.              */
+ * 3 pd_explicit_run, 4 pd_diag_run -- lets a foreign-language binding verify its struct layout.              */
 int pd_struct_size(int which);
 
 /* ---- flow compiler back end -------------------------------------------------------------- */
@@ -138,6 +154,8 @@ int pd_explicit_schedule(int32_t n_time, const double *target_times, double min_
 int pd_run_explicit(pd_model *m, const pd_explicit_run *run, pd_run_result *res);
 int pd_run_tau_leap(pd_model *m, const pd_stoch_run *run, pd_run_result *res);
 int pd_run_gillespie(pd_model *m, const pd_stoch_run *run, pd_run_result *res);
+/* replaces BaseModel.calculate_diagnostics (basepop.py:911-960) for a batch of members */
+int pd_run_diagnostics(pd_model *m, const pd_diag_run *run, pd_run_result *res);
 
 /* ---- ensemble statistics ------------------------------------------------------------------ */
 /* Quantiles from (all-reduced) histograms: for every (row, c) and every q the smallest bin b with

@@ -16,7 +16,7 @@ import numpy
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libpopdyn_b200.so')
 
-EXPLICIT, TAU_LEAP, GILLESPIE = 0, 1, 2
+EXPLICIT, TAU_LEAP, GILLESPIE, DIAGNOSTICS = 0, 1, 2, 3
 FULL, FINAL, STATS = 0, 1, 2
 PHILOX, INJECT = 0, 1
 METHOD_CODES = {'explicit': EXPLICIT, 'discrete_time_stochastic': TAU_LEAP,
@@ -36,8 +36,8 @@ DEVICE_ERRORS = {
 EXPORTED_SYMBOLS = (
     'pd_version', 'pd_last_error', 'pd_device_count', 'pd_struct_size', 'pd_model_create', 'pd_model_destroy',
     'pd_model_cubin_size', 'pd_model_cubin_copy', 'pd_explicit_schedule', 'pd_run_explicit',
-    'pd_run_tau_leap', 'pd_run_gillespie', 'pd_hist_quantiles', 'pd_philox_fill',
-    'pd_microbench')
+    'pd_run_tau_leap', 'pd_run_gillespie', 'pd_run_diagnostics', 'pd_hist_quantiles',
+    'pd_philox_fill', 'pd_microbench')
 
 
 class ExtensionMissing(RuntimeError):
@@ -87,6 +87,14 @@ class ExplicitRun(C.Structure):
                 ('soln', C.c_void_p), ('final_state', C.c_void_p), ('stream', C.c_void_p)]
 
 
+class DiagRun(C.Structure):
+    _fields_ = [('n_member', C.c_int64), ('n_time', C.c_int32), ('n_var', C.c_int32),
+                ('soln', C.c_void_p), ('uniform_params', C.c_void_p),
+                ('member_params', C.c_void_p), ('times', C.c_void_p),
+                ('scaleup_row', C.c_void_p), ('var_soln', C.c_void_p),
+                ('flow_soln', C.c_void_p), ('stream', C.c_void_p)]
+
+
 _lib = None
 
 
@@ -117,6 +125,7 @@ def lib():
     L.pd_run_explicit.argtypes = [C.c_void_p, P(ExplicitRun), P(RunResult)]
     L.pd_run_tau_leap.argtypes = [C.c_void_p, P(StochRun), P(RunResult)]
     L.pd_run_gillespie.argtypes = [C.c_void_p, P(StochRun), P(RunResult)]
+    L.pd_run_diagnostics.argtypes = [C.c_void_p, P(DiagRun), P(RunResult)]
     L.pd_hist_quantiles.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     L.pd_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64,
@@ -200,7 +209,8 @@ def run(model, run_struct):
     caller decides which Python exception it maps to."""
     res = RunResult()
     fn = {EXPLICIT: lib().pd_run_explicit, TAU_LEAP: lib().pd_run_tau_leap,
-          GILLESPIE: lib().pd_run_gillespie}[model.desc.method]
+          GILLESPIE: lib().pd_run_gillespie,
+          DIAGNOSTICS: lib().pd_run_diagnostics}[model.desc.method]
     status = fn(model.handle, C.byref(run_struct), C.byref(res))
     if status != 0 and status != PD_E_MODEL:
         check(status)

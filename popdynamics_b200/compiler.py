@@ -420,6 +420,10 @@ class CompiledModel(object):
         self.check_nodes = []
         self.uses_time = False
         self.var_nodes = {}        # var label -> node id (all vars seen in the trace)
+        self.diagnostics = False   # compiled for the diagnostics pass (basepop.py:911-960)
+        self.diag_labels = []      # var_labels of the diagnostics pass, in the reference's order
+        self.diag_nodes = []       # node of every diagnostic var
+        self.diag_flow_nodes = []  # net flow of every compartment (flow_array)
 
     # ---- sizes
     @property
@@ -527,13 +531,22 @@ class _Tracer(object):
         return self.param_symbol('<%s>' % tag, value)
 
 
-def compile_model(model, method, is_continue=False, naive_sum=None):
+def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=False):
     """Lower ``model`` for ``method`` ('explicit', 'discrete_time_stochastic',
     'continuous_time_stochastic').  ``model.set_flows()`` must already have run
-    (``check_flow_transfers``, basepop.py:638-656)."""
+    (``check_flow_transfers``, basepop.py:638-656).
+
+    ``diagnostics=True`` lowers the diagnostics pass instead (``calculate_diagnostics``,
+    basepop.py:911-960): at every stored time the compartments are the ``numpy.float64`` values
+    of ``soln_array`` -- floats whatever the integrator was, so ``old_div`` divides truly and
+    ``sum`` folds naively -- then ``calculate_vars``, ``calculate_flows`` and the
+    ``calculate_diagnostic_vars`` hook run; every numeric entry of ``self.vars`` is an output
+    (``var_array``) and so is the net flow of every compartment (``flow_array``)."""
     from .basepop import BaseModel
 
-    integer_state = method != 'explicit'
+    integer_state = method != 'explicit' and not diagnostics
+    if diagnostics:
+        naive_sum = True
     if naive_sum is None:
         # after is_continue the compartments are numpy.float64 (basepop.py:932-933) and Python's
         # sum() falls off its compensated float fast path
@@ -545,6 +558,7 @@ def compile_model(model, method, is_continue=False, naive_sum=None):
     cm.method = method
     cm.integer_state = integer_state
     cm.naive_sum = naive_sum
+    cm.diagnostics = bool(diagnostics)
     cm.graph = g
     index_of = {label: i for i, label in enumerate(cm.labels)}
 
@@ -599,7 +613,8 @@ def compile_model(model, method, is_continue=False, naive_sum=None):
 
     saved = dict(params=model.params, compartments=model.compartments, vars=model.vars,
                  time=model.time, fixed=model.fixed_transfer_rate_flows,
-                 inf=model.infection_death_rate_flows, bg=model.background_death_rate)
+                 inf=model.infection_death_rate_flows, bg=model.background_death_rate,
+                 flows=model.flows)
     try:
         model.params = _ParamView(tr, saved['params'])
         model.compartments = comps
@@ -611,6 +626,10 @@ def compile_model(model, method, is_continue=False, naive_sum=None):
             model.background_death_rate = bg_sym
         if method != 'explicit':
             model.calculate_scaleup_vars = traced_scaleup_vars
+        else:
+            # a hook that calls it again re-reads the values of this sub-step (host table)
+            su_syms = dict(traced_vars)
+            model.calculate_scaleup_vars = lambda: model.vars.update(su_syms)
         try:
             with _patched_sum(naive_sum):
                 model.calculate_vars()
@@ -676,6 +695,22 @@ def compile_model(model, method, is_continue=False, naive_sum=None):
             cm.check_nodes = list(g.assertions)
         cm.var_nodes = {k: as_sym(v, 'vars[%r]' % k).n for k, v in hook_vars.items()
                         if isinstance(v, (Sym, numbers.Real)) and not getattr(v, 'is_bool', False)}
+
+        # ---- diagnostics pass: calculate_flows + the diagnostic hook on the traced state -----
+        if diagnostics:
+            model.vars = dict(hook_vars)
+            model.flows = {}
+            with _patched_sum(naive_sum):
+                model.calculate_flows()                  # basepop.py:560-598, incl. rate_death
+                model.calculate_diagnostic_vars()        # hook, basepop.py:905
+            for label, value in model.vars.items():
+                if isinstance(value, Sym) and value.is_bool:
+                    continue
+                if isinstance(value, (Sym, numbers.Real)) and not isinstance(value, bool):
+                    cm.diag_labels.append(label)
+                    cm.diag_nodes.append(as_sym(value, 'vars[%r]' % label).n)
+            cm.diag_flow_nodes = [as_sym(model.flows[label], 'flows[%r]' % label).n
+                                  for label in cm.labels]
     finally:
         model.params = saved['params']
         model.compartments = saved['compartments']
@@ -684,13 +719,15 @@ def compile_model(model, method, is_continue=False, naive_sum=None):
         model.fixed_transfer_rate_flows = saved['fixed']
         model.infection_death_rate_flows = saved['inf']
         model.background_death_rate = saved['bg']
+        model.flows = saved['flows']
 
     cm.param_labels = tr.param_labels
     cm.param_values = tr.param_values
     cm.param_is_int = tr.param_is_int
 
     # ---- dead-code elimination + evaluation order --------------------------------------------
-    roots = list(cm.flow_node) + list(cm.check_nodes)
+    roots = list(cm.flow_node) + list(cm.check_nodes) + list(cm.diag_nodes) + \
+        list(cm.diag_flow_nodes)
     live = set()
     stack = list(roots)
     while stack:

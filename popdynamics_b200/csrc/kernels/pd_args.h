@@ -17,6 +17,7 @@
 #define PD_METHOD_EXPLICIT 0
 #define PD_METHOD_TAU_LEAP 1
 #define PD_METHOD_GILLESPIE 2
+#define PD_METHOD_DIAGNOSTICS 3
 
 #define PD_MAX_HIST_COMP 64
 
@@ -92,5 +93,17 @@ typedef struct {
   int n_time;
   int pad;
 } PdExplicitArgs;
+
+typedef struct {
+  long long n_member;
+  const double *soln;          /* [T][C][M] stored compartments                                  */
+  const double *pm;            /* per-member parameters [PD_NPM][M]                              */
+  const double *times;         /* [T] stored times                                               */
+  const double *su;            /* [PD_NSU] scale-up values of the last derivative call, or NULL  */
+  double *var_soln;            /* [T][PD_NDIAG][M]                                               */
+  double *flow_soln;           /* [T][C][M] or NULL                                              */
+  int n_time;
+  int pad;
+} PdDiagArgs;
 
 #endif

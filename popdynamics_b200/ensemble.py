@@ -365,6 +365,99 @@ def integrate_ensemble(model, method='explicit', n_members=None, output='full', 
     return res
 
 
+class DiagnosticsResult(object):
+    """Outputs of the batched diagnostics pass: ``var_labels`` in the reference's order,
+    ``vars`` [T][V][M] (``var_array`` of every member), ``flows`` [T][C][M] (``flow_array``) or
+    None.  For a final-state input T is 1 and the arrays are [V][M] / [C][M]."""
+
+    def __init__(self):
+        self.var_labels, self.labels, self.times = [], [], None
+        self.vars, self.flows, self.info = None, None, {}
+
+    def var(self, label):
+        """[T][M] (or [M]) slice of one var, e.g. ``var('proportion')``."""
+        k = self.var_labels.index(label)
+        return self.vars[:, k] if self.vars.ndim == 3 else self.vars[k]
+
+    def fraction(self, label, soln):
+        """``fraction_soln[label]`` of every member (basepop.py:954-960): compartment over
+        vars['population']."""
+        c = self.labels.index(label)
+        return soln[..., c, :] / self.var('population')
+
+
+def diagnostics(model, result, method=None, want_flows=False, device=None, block=256):
+    """The diagnostics pass (``calculate_diagnostics``, /root/reference/basepop.py:911-960) for
+    every member of an ensemble result: ``calculate_vars`` / ``calculate_flows`` /
+    ``calculate_diagnostic_vars`` traced once and evaluated on the device at every stored time
+    of ``result.soln`` ([T][C][M]) or on ``result.final`` ([C][M]).  ``model`` must still carry
+    the parameters (incl. per-member arrays) the result was produced with.
+
+    Scale-up vars: for the explicit integrator the reference never re-evaluates them in this pass,
+    they keep the value of the last derivative call -- reproduced here; a hook
+    that calls ``calculate_scaleup_vars()`` itself gets them at the stored time."""
+    method = method or result.method
+    device = result.device if device is None else device
+    model.check_flow_transfers()
+    cm = compiler.compile_model(model, method, diagnostics=True)
+    if not cm.diag_nodes:
+        raise ValueError('the model defines no vars')
+    soln = result.soln if result.soln is not None else result.final
+    if soln is None:
+        raise ValueError("diagnostics need output='full' or output='final'")
+    final_only = result.soln is None
+    M = int(result.n_members)
+    C, V = cm.n_comp, len(cm.diag_nodes)
+    times = numpy.ascontiguousarray(result.times[-1:] if final_only else result.times,
+                                    dtype=numpy.float64)
+    T = len(times)
+    source = cm.cuda_source()
+    key = (source, capi.DIAGNOSTICS, device, block)
+    kernel = _KERNEL_CACHE.get(key)
+    if kernel is None:
+        kernel = capi.Model(source, capi.DIAGNOSTICS, capi.FULL, capi.PHILOX, device, C,
+                            cm.n_param, len(cm.member_param_slots()), cm.n_su, cm.n_flow,
+                            block=block)
+        _KERNEL_CACHE[key] = kernel
+    out = DiagnosticsResult()
+    out.var_labels, out.labels, out.times = list(cm.diag_labels), list(cm.labels), times
+
+    def like(shape):
+        if _is_torch(soln):
+            import torch
+            return torch.empty(shape, dtype=torch.float64, device=soln.device)
+        return numpy.empty(shape, dtype=numpy.float64)
+
+    out.vars = like((T, V, M))
+    out.flows = like((T, C, M)) if want_flows else None
+    run = capi.DiagRun()
+    run.n_member, run.n_time, run.n_var = M, T, V
+    run.soln = capi.address(soln)
+    uniform = cm.uniform_params()
+    member_params = _member_param_block(cm, M)
+    su_row = None
+    if cm.n_su:
+        t_last = result.info.get('last_eval_time')
+        if t_last is None:
+            raise ValueError('the result does not record the time of the last derivative call')
+        su_row = numpy.array([model.scaleup_fns[label](t_last) for label in cm.su_labels],
+                             dtype=numpy.float64)
+    keep = [uniform, member_params, su_row, times]
+    run.uniform_params = capi.address(uniform)
+    run.member_params = capi.address(member_params)
+    run.times = capi.address(times)
+    run.scaleup_row = capi.address(su_row)
+    run.var_soln = capi.address(out.vars)
+    run.flow_soln = capi.address(out.flows)
+    res = capi.run(kernel, run)
+    out.info = res.as_dict()
+    del keep
+    if final_only:
+        out.vars = out.vars[0]
+        out.flows = out.flows[0] if want_flows else None
+    return out
+
+
 def pilot_hist_max(model, method, n_pilot=2048, seed=12345, margin=1.5, device=None):
     """Largest count per compartment over a small pilot ensemble, times ``margin``: a bound for
     ``hist_max`` when nothing better is known."""

@@ -51,7 +51,8 @@ def test_structs_match_the_compiled_layout(built_library):
     assert ctypes.sizeof(capi.RunResult) == size(1)
     assert ctypes.sizeof(capi.StochRun) == size(2)
     assert ctypes.sizeof(capi.ExplicitRun) == size(3)
-    assert size(4) == -1
+    assert ctypes.sizeof(capi.DiagRun) == size(4)
+    assert size(5) == -1
 
 
 @pytest.mark.skipif(capi.lib().pd_device_count() > 0, reason='a GPU is present')

@@ -362,3 +362,65 @@ def test_resident_torch_buffers_are_used_in_place():
     m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='stats', seed=4,
                          moments=moments)
     assert np.array_equal(moments[..., 0].cpu().numpy(), host.soln.sum(axis=2).astype(np.int64))
+
+
+# ------------------------------------------------------------------------------- diagnostics
+def _host_diagnostics(make_member_model, method, times, trajectory, info=None):
+    """The drop-in's own calculate_diagnostics (the reference's algorithm, basepop.py:911-960,
+    golden-tested against the reference) on one member's stored trajectory."""
+    m = make_member_model()
+    m.make_times(*times)
+    m.check_flow_transfers()
+    m.soln_array = np.array(trajectory)
+    m.times = list(m.target_times)
+    if info is not None and m.scaleup_fns:
+        # the reference leaves the scale-up vars of the LAST derivative call in self.vars
+        m.time = info['last_eval_time']
+        m.calculate_scaleup_vars()
+    m.calculate_diagnostics()
+    return m
+
+
+@pytest.mark.parametrize('method', ['explicit', 'discrete_time_stochastic',
+                                    'continuous_time_stochastic'])
+def test_batched_diagnostics_equal_the_host_pass_per_member(method):
+    n = 150
+    r0 = np.linspace(2.5, 4.0, n)
+    times = (0, 40, 1)
+    m = helpers.make_model('strains', params=[('r0_invader', r0)])
+    m.make_times(*times)
+    res = m.integrate_ensemble(method, output='full', seed=3)
+    diag = ensemble.diagnostics(m, res, want_flows=True)
+    assert diag.vars.shape == (41, len(diag.var_labels), n)
+    for i in (0, 77, n - 1):
+        host = _host_diagnostics(
+            lambda: helpers.make_model('strains', params=[('r0_invader', float(r0[i]))]),
+            method, times, res.soln[:, :, i])
+        assert diag.var_labels == host.var_labels
+        assert np.array_equal(diag.vars[:, :, i], host.var_array)
+        assert np.array_equal(diag.flows[:, :, i], host.flow_array)
+        frac = diag.fraction('susceptible', res.soln)[:, i]
+        assert np.array_equal(frac, np.array(host.fraction_soln['susceptible']))
+
+
+def test_batched_diagnostics_final_state_sweep_and_stale_scaleups(golden):
+    # BASELINE config 5 reads model.vars['proportion'] of the final state (rmit_tb_model.py:143)
+    betas = golden['rmit_sweep_betas']
+    m = helpers.make_model('rmit', params=dict(sigma1=0.25, sigma2=0.125, sigma3=0.125, tau=2.,
+                                               beta=betas.copy(), rho=0.5))
+    m.make_times(0, 500., 1.)
+    res = m.integrate_ensemble('explicit', output='final')
+    diag = ensemble.diagnostics(m, res)
+    final = golden['rmit_sweep_final']                               # [n][C] from the reference
+    # numpy.float64 compartments: Python's sum() is the plain left fold there
+    population = np.array([sum(np.float64(v) for v in row) for row in final])
+    want = final[:, 4] / population
+    assert np.array_equal(diag.var('proportion'), want)
+    assert diag.vars.shape == (len(diag.var_labels), len(betas))
+    # TB model: the scale-up var keeps the value of the last derivative call (SURVEY.md 3.4)
+    m = helpers.make_model('tb')
+    m.make_times(1900, 2050, .05)
+    res = m.integrate_ensemble('explicit', n_members=3, output='full')
+    diag = ensemble.diagnostics(m, res)
+    assert diag.var_labels == list(golden['tb_var_labels'])
+    assert np.array_equal(diag.vars[::50, :, 1], golden['tb_var_array_every50'])
