@@ -86,7 +86,8 @@ typedef struct {
   const double *uniforms; int64_t n_uniform;           /* PD_INJECT: [n_uniform][M]           */
   double *soln;                   /* PD_FULL  [T][C][M]                                       */
   double *final_state;            /* PD_FINAL [C][M]                                          */
-  uint64_t *moments;              /* PD_STATS [T][C][2], ACCUMULATED into (caller zeroes)     */
+  uint64_t *moments;              /* PD_STATS [T][C][2] = (sum x, sum x^2), exact while they fit
+                                     64 bits; ACCUMULATED into (caller zeroes)                */
   uint32_t *hist;                 /* PD_STATS [n_hist_row][C][hist_bins] or NULL, accumulated */
   const int32_t *hist_row;        /* [T] HOST: row per target index or -1                     */
   const int32_t *hist_shift;      /* [C] HOST: bin = min(count >> shift, bins - 1)            */

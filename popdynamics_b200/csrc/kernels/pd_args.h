@@ -64,18 +64,14 @@ typedef struct {
 #define PD_RING_EPOCH 4  /* lane-asynchronous recording (Gillespie): ring of parked counts    */
 #endif
 
-/* Dynamic shared memory of the stochastic kernels, in this order (host and device agree through
- * these macros):
- *   tau-leap only: event codes  double   [n_row][block]      (n_row = live flow-table rows)
- *   counts ring                 count_t  [n_slot][n_comp][block]
- *                               n_slot = PD_EPOCH for PD_OUT_STATS, 1 for tau-leap otherwise,
- *                               0 for Gillespie otherwise (counts stay in registers)
- *   tau-leap only: event table  uint32   [n_row] (padded to 8 bytes)                          */
+/* Dynamic shared memory of the stochastic kernels (each kernel exports its total as the device
+ * symbol pd_smem_bytes, which the host reads after loading the module):
+ *   tau-leap : the draw list     double   [n_row][block]   (n_row = flow-table rows that can fire)
+ *   Gillespie, PD_OUT_STATS: counts ring  count_t [PD_RING_EPOCH][n_comp][block]              */
 #define PD_ALIGN8(x) (((x) + 7) & ~(size_t)7)
 #define PD_CODE_SMEM_BYTES(n_row, block) ((size_t)((n_row) > 0 ? (n_row) : 1) * (size_t)(block) * 8)
 #define PD_RING_SMEM_BYTES(n_slot, n_comp, block, count_bytes)                             \
   PD_ALIGN8((size_t)(n_slot) * (size_t)(n_comp) * (size_t)(block) * (size_t)(count_bytes))
-#define PD_TAB_SMEM_BYTES(n_row) PD_ALIGN8((size_t)((n_row) > 0 ? (n_row) : 1) * 4)
 
 typedef struct {
   long long n_member;

@@ -272,6 +272,14 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
             if hist_max is None:
                 raise ValueError('hist_max (largest expected count per compartment) is needed '
                                  'with hist_bins; see ensemble.pilot_hist_max')
+            # the second moment is an exact u64 sum of x^2 over ALL members that accumulate into
+            # this buffer: refuse a launch that could overflow it on its own
+            worst = float(numpy.max(numpy.asarray(hist_max, dtype=numpy.float64)))
+            if float(M) * worst * worst >= 2.0 ** 64:
+                raise ValueError(
+                    'n_members * hist_max^2 = %.3g does not fit the exact 64-bit second moment; '
+                    'run the ensemble in smaller launches with separate moment buffers and add '
+                    'them as Python integers' % (float(M) * worst * worst))
             row, shift, rows = _hist_setup(T, C, hist_bins, hist_max, hist_times)
             if hist is not None:
                 res.hist = hist
