@@ -78,7 +78,7 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
 #define PD_G1_ENTRY(e, to, is_int, rate) r[e] = rate; PD_ACC(e, is_int)
 #define PD_G1_TRANSFER(e, from, to, rate) r[e] = rate; if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
 #define PD_G1_DEATH(e, from, rate) r[e] = rate; if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
-  PD_FOR_EACH_FLOW(PD_G1_ENTRY, PD_G1_TRANSFER, PD_G1_DEATH)
+  PD_FOR_EACH_LIVE_ROW(PD_G1_ENTRY, PD_G1_TRANSFER, PD_G1_DEATH)
 #undef PD_G1_ENTRY
 #undef PD_G1_TRANSFER
 #undef PD_G1_DEATH
@@ -109,7 +109,7 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
 #define PD_G2_ENTRY(e, to, is_int, rate) if (sel < 0 && !(point > cumul[e])) sel = e;
 #define PD_G2_TRANSFER(e, from, to, rate) PD_PICK(e)
 #define PD_G2_DEATH(e, from, rate) PD_PICK(e)
-  PD_FOR_EACH_FLOW(PD_G2_ENTRY, PD_G2_TRANSFER, PD_G2_DEATH)
+  PD_FOR_EACH_LIVE_ROW(PD_G2_ENTRY, PD_G2_TRANSFER, PD_G2_DEATH)
 #undef PD_G2_ENTRY
 #undef PD_G2_TRANSFER
 #undef PD_G2_DEATH
@@ -120,7 +120,7 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
 #define PD_G3_ENTRY(e, to, is_int, rate) if (sel == e) y[to] += 1;
 #define PD_G3_TRANSFER(e, from, to, rate) if (sel == e) { y[from] -= 1; y[to] += 1; }
 #define PD_G3_DEATH(e, from, rate) if (sel == e) y[from] -= 1;
-  PD_FOR_EACH_FLOW(PD_G3_ENTRY, PD_G3_TRANSFER, PD_G3_DEATH)
+  PD_FOR_EACH_LIVE_ROW(PD_G3_ENTRY, PD_G3_TRANSFER, PD_G3_DEATH)
 #undef PD_G3_ENTRY
 #undef PD_G3_TRANSFER
 #undef PD_G3_DEATH
@@ -178,35 +178,37 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
     const int it1 = (it0 + PD_RING_EPOCH < a.n_time) ? it0 + PD_RING_EPOCH : a.n_time;
     if (active) {
       int it = it0;
-      while (it < it1) {
-        if (it > 0 && !bad && time < a.target[it]) {        /* :762 */
-          bad = pd_gillespie_event(a, L.U, pm, y, time, a.target[it], rng, n_event);
-        } else {
+      for (;;) {
+        while (it < it1 && (it == 0 || bad || !(time < a.target[it]))) {
 #pragma unroll
           for (int c = 0; c < PD_C; ++c)
             s_ring[((it - it0) * PD_C + c) * PD_BLOCK + threadIdx.x] = y[c];   /* :793-795 */
           ++it;
         }
+        if (it >= it1) break;
+        bad = pd_gillespie_event(a, L.U, pm, y, time, a.target[it], rng, n_event);   /* :762 */
       }
     }
     pd_stats_flush(a, s_ring, it0, it1 - it0, n_active, a.member0 + block_member0);
   }
 #else
   if (active) {
+    /* Every trip of the loop is one reaction for EVERY unfinished lane: a lane first steps over
+     * the target times it has already reached (a short predicated loop, usually no trip), so
+     * that recording never takes a warp-wide turn of its own. */
     int it = 1;
-    while (it < a.n_time) {
-      const double new_time = a.target[it];
-      if (time < new_time) {                                /* :762 */
-        bad = pd_gillespie_event(a, L.U, pm, y, time, new_time, rng, n_event);
-        if (bad) break;
-      } else {
+    for (;;) {
+      while (it < a.n_time && !(time < a.target[it])) {      /* :762 false -> record, :793-795 */
 #if PD_OUT_MODE == PD_OUT_FULL
 #pragma unroll
         for (int c = 0; c < PD_C; ++c)
-          a.soln[((size_t)it * PD_C + c) * M + m] = (double)y[c];   /* :793-795 */
+          a.soln[((size_t)it * PD_C + c) * M + m] = (double)y[c];
 #endif
         ++it;
       }
+      if (it >= a.n_time) break;
+      bad = pd_gillespie_event(a, L.U, pm, y, time, a.target[it], rng, n_event);
+      if (bad) break;
     }
   }
 #endif

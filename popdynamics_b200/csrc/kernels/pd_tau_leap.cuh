@@ -35,9 +35,9 @@ struct PdTauLaunch {
   PdUniform U;
 };
 
-#if PD_TAU_NROW <= 32
+#if PD_LIVE_NROW <= 32
 typedef pd_u32 pd_mask;
-#elif PD_TAU_NROW <= 64
+#elif PD_LIVE_NROW <= 64
 typedef pd_u64 pd_mask;
 #else
 #error "the tau-leap kernel handles at most 64 flow-table rows"
@@ -46,7 +46,7 @@ typedef pd_u64 pd_mask;
 /* the kernel's dynamic shared memory (the draw list), read by the host after loading the module
  * (csrc/popdyn_capi.cu) */
 extern "C" __device__ unsigned int pd_smem_bytes =
-    (unsigned int)PD_CODE_SMEM_BYTES(PD_TAU_NROW, PD_BLOCK);
+    (unsigned int)PD_CODE_SMEM_BYTES(PD_LIVE_NROW, PD_BLOCK);
 
 /* a finished draw is parked in the list cell of its code; with 32-bit counts it saturates at
  * 2^31 - 1, which changes nothing: a clamp brings it down to a count anyway and an unclamped
@@ -128,7 +128,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
 #define PD_TAU_DEATH(e, from, rate)                                                  \
   { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
-      PD_FOR_EACH_TAU_ROW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
+      PD_FOR_EACH_LIVE_ROW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
 #undef PD_TAU_ENTRY
 #undef PD_TAU_TRANSFER
 #undef PD_TAU_DEATH
@@ -215,7 +215,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   { PD_TAU_TAKE(e, d) d = d < y[from] ? d : y[from]; y[from] -= d; y[to] += d; signs |= y[to]; }
 #define PD_TAU_DEATH(e, from, rate)                                                  \
   { PD_TAU_TAKE(e, d) d = d < y[from] ? d : y[from]; y[from] -= d; }
-        PD_FOR_EACH_TAU_ROW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
+        PD_FOR_EACH_LIVE_ROW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
 #undef PD_TAU_ENTRY
 #undef PD_TAU_TRANSFER
 #undef PD_TAU_DEATH

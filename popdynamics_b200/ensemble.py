@@ -187,9 +187,11 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
     method_code = capi.METHOD_CODES[method]
     out_code = capi.OUTPUT_CODES[output]
     rng_code = capi.INJECT if uniforms is not None else capi.PHILOX
-    if not min_blocks and method == 'discrete_time_stochastic':
-        # measured on B200 (profiles/): the tau-leap kernel is fastest at 64 registers per thread,
-        # i.e. 1024 resident threads per SM, whatever the block size
+    if not min_blocks and (method == 'discrete_time_stochastic' or
+                           (method == 'continuous_time_stochastic' and cm.n_flow <= 16)):
+        # measured on B200 (profiles/): the stochastic kernels are fastest at 64 registers per
+        # thread, i.e. 1024 resident threads per SM, whatever the block size; the Gillespie
+        # kernel of a large flow table (TB: 20 rows, 84 registers) is better left uncapped
         min_blocks = max(1, 1024 // int(block))
     kernel = _kernel_for(cm, method_code, out_code, rng_code, device, count_bits, block,
                          min_blocks)

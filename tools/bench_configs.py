@@ -48,6 +48,12 @@ CONFIGS = {
                           (0, 1000, 1), 1 << 20, 'stats', 2000),
     'strains_dts_full': (lambda n, rng: models.StrainsModel(), 'discrete_time_stochastic',
                          (0, 200, 1), 1 << 20, 'full', 2000),
+    # BASELINE config 4: TB model with its scale-ups evaluated inside the stochastic loops
+    # (population 1e6: ~6e4 events per member-year; every tau-leap mean is in the PTRS branch)
+    'tb_cts': (lambda n, rng: models.ScaleupTbModel([]), 'continuous_time_stochastic',
+               (1950, 1951, 1.), 1 << 16, 'final', 64),
+    'tb_dts': (lambda n, rng: models.ScaleupTbModel([]), 'discrete_time_stochastic',
+               (1950, 2000, 1.), 1 << 20, 'final', 20000),
 }
 
 
