@@ -144,6 +144,16 @@ class OracleModel(object):
                                float(min_dt), _ptr(su), _ptr(soln), C.byref(err))
         return soln, int(n), err.value
 
+    def explicit_first_failure(self, y0, target_times, params=None, min_dt=0.05, su_table=None):
+        """Target index of the interval in which checks() first fails, 0 if never."""
+        tt = _f64(target_times)
+        p = _f64(self.member_params() if params is None else params)
+        su = None if su_table is None else _f64(su_table)
+        fn = lib().pdo_explicit_first_failure
+        fn.restype = C.c_int32
+        return int(fn(C.byref(self.struct), _ptr(_f64(y0)), _ptr(p), len(tt), _ptr(tt),
+                      C.c_double(float(min_dt)), _ptr(su)))
+
     def _stochastic(self, fn, y0, target_times, rng, params):
         tt = _f64(target_times)
         p = _f64(self.member_params() if params is None else params)

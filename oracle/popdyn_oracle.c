@@ -348,6 +348,40 @@ static void calc_flows(const pdo_model *m, const double *y, const double *v, dou
   }
 }
 
+/* Target index of the interval in which checks() first fails (basepop.py:623 inside the loop of
+ * :672-688), 0 when it never does: the index the device error flag has to report.             */
+int32_t pdo_explicit_first_failure(const pdo_model *m, const double *y0, const double *params,
+                                   int32_t n_time, const double *target, double min_dt,
+                                   const double *su_table) {
+  const int C = m->n_comp;
+  double *v = (double *)malloc(sizeof(double) * (size_t)n_values(m));
+  double *y = (double *)malloc(sizeof(double) * (size_t)C);
+  double *f = (double *)malloc(sizeof(double) * (size_t)C);
+  int64_t n_step = 0;
+  int32_t where = 0;
+  for (int i = 0; i < C; i++) y[i] = y0[i];
+  double time = target[0];
+  for (int32_t it = 1; it < n_time && !where; it++) {
+    double new_time = target[it];
+    while (time < new_time) {
+      pdo_eval_vars(m, y, params, time, su_table ? su_table + n_step * m->n_su : 0, v);
+      calc_flows(m, y, v, f);
+      if (run_checks(m, v)) { where = it; break; }
+      double old_time = time;
+      time = time + min_dt;
+      double dt = min_dt;
+      if (time > new_time) { dt = new_time - old_time; time = new_time; }
+      for (int i = 0; i < C; i++) {
+        y[i] = y[i] + dt * f[i];
+        if (y[i] < 0.) y[i] = 0.;
+      }
+      n_step++;
+    }
+  }
+  free(v); free(y); free(f);
+  return where;
+}
+
 int64_t pdo_explicit(const pdo_model *m, const double *y0, const double *params,
                      int32_t n_time, const double *target, double min_dt,
                      const double *su_table, double *soln, int32_t *err) {

@@ -77,6 +77,9 @@ int32_t pdo_pick_event(const double *intervals, int32_t n, double u); /* basepop
  * rate, 4 uniform stream exhausted, 5 log(0)                                               */
 int64_t pdo_explicit_schedule(int32_t n_time, const double *target, double min_dt,
                               double *t_eval, double *dt, int32_t *interval, int64_t cap);
+int32_t pdo_explicit_first_failure(const pdo_model *m, const double *y0, const double *params,
+                                   int32_t n_time, const double *target, double min_dt,
+                                   const double *su_table);
 int64_t pdo_explicit(const pdo_model *m, const double *y0, const double *params,
                      int32_t n_time, const double *target, double min_dt,
                      const double *su_table, double *soln, int32_t *err);

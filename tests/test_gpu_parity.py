@@ -135,6 +135,26 @@ def test_device_checks_raise_assertionerror():
         m.integrate()
 
 
+def test_default_checks_report_the_reference_failure_index():
+    # explicit Euler at dt = .05 diverges for these RMIT parameters: the compartments overflow to
+    # NaN and the default checks() (basepop.py:1023-1025) fails; the target index the device error
+    # flag reports must be the one at which the reference's per-sub-step assert fires.
+    cases = [dict(rho=0.4675096681435942, sigma1=0.4864215594357471, sigma2=0.40346161064467484,
+                  sigma3=0.40408850758699627, beta=462.931574029995),
+             dict(rho=6.022910254870821, sigma1=0.4835608014116187, sigma2=0.2066750375597674,
+                  sigma3=0.2580841604166728, beta=498.5081362431734)]
+    for params in cases:
+        m = helpers.make_model('rmit', params=params)
+        m.make_times(0, 500., 1.)
+        om = oracle.OracleModel(helpers.compiled(m, 'explicit'))
+        want = om.explicit_first_failure(m.get_init_list(), m.target_times)
+        assert want > 0
+        res = m.integrate_ensemble('explicit', n_members=5, output='final', check=False)
+        assert res.info['err_code'] == 1 and res.info['err_where'] == want
+        with pytest.raises(AssertionError, match='target index %d' % want):
+            m.integrate_ensemble('explicit', n_members=5, output='final')
+
+
 # ------------------------------------------------------------------------------- stochastic
 def _inject(method, model_name, n_member, n_uniform, times, seed, params=None):
     m = helpers.make_model(model_name, **({'params': params} if params else {}))

@@ -1,1 +1,7 @@
-for cfg in "final 256 1" "final 256 3" "final 256 4" "final 128 8" "final 128 6" "stats 256 3" "stats 256 4" "stats 256 1"; do set -- $cfg; python tools/run_one.py cts $1 32 $2 $3 1048576 1000 2 2>&1 | tail -1; done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/bench_configs.py sir seir rmit 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(d['config'], 'regs', d['regs'], 'ms %.2f'%d['kernel_ms'], 'steps/s %.4g'%d['steps_per_s'])
+    else: print(l.rstrip())"
