@@ -52,6 +52,12 @@ typedef struct {
   int hist_shift[PD_MAX_HIST_COMP]; /* bin = min(count >> shift[c], bins - 1)                    */
   unsigned int philox_rk[20];  /* Philox round keys (k0, k1) of rounds 0..9, filled by the host
                                   from `seed`: operands straight from the constant bank          */
+  const double *code_table;    /* tau-leap: [PD_NTAB][code_table_n] Poisson codes by count, built
+                                  by pd_tau_table_kernel when every step has the same dt; NULL
+                                  otherwise                                                      */
+  double code_table_dt;        /* the dt the table was built for                                 */
+  int code_table_n;
+  int pad1;
 } PdStochArgs;
 
 /* Streaming statistics are reduced once per EPOCH of PD_EPOCH recorded target times: a lane keeps

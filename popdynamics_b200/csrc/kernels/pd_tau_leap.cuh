@@ -48,6 +48,49 @@ typedef pd_u64 pd_mask;
 extern "C" __device__ unsigned int pd_smem_bytes =
     (unsigned int)PD_CODE_SMEM_BYTES(PD_LIVE_NROW, PD_BLOCK);
 
+/* Poisson code of a mean: exp(-mean) for the multiplication method, -mean for PTRS */
+__device__ __forceinline__ double pd_tau_code(double mean) {
+  return (mean >= 10.0) ? -mean : pd_exp_nonpos(-mean);
+}
+
+/* Code tables (see codegen.py): a row whose rate is count * U.p[k] has a code that is a function of
+ * the integer count alone while dt is constant.  This kernel evaluates exactly the expression of
+ * the rate pass -- rate = (double)n * p; mean = rate * dt; pd_tau_code(mean) -- for n = 0 ..
+ * n_entry - 1, so a looked-up code is bit-identical to a computed one.  0.0 marks "the row does
+ * not exist / draws nothing" (:712-733, a zero mean), NaN a negative or NaN mean (error). */
+extern "C" __device__ unsigned int pd_tab_count = PD_NTAB;       /* tables of n_entry codes  */
+extern "C" __device__ unsigned int pd_uni_count = PD_NUNI;       /* single codes behind them */
+__device__ const int pd_tab_param[PD_NTAB_DIM] = PD_TAB_PARAMS;
+
+extern "C" __global__ void pd_tau_table_kernel(const __grid_constant__ PdTauLaunch L, double *table,
+                                               int n_entry, double dt) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n == 0) {
+    /* entry rows with an ensemble-wide rate: one code each (basepop.py:706-707, always present;
+     * a zero mean draws nothing) */
+    const PdUniform &U = L.U;
+    const double uni_rate[PD_NUNI_DIM] = PD_UNI_RATES;
+    for (int j = 0; j < PD_NUNI; ++j) {
+      const double mean = uni_rate[j] * dt;
+      double code = 0.0;
+      if (mean > 0.0) code = pd_tau_code(mean);
+      else if (!(mean == 0.0)) code = __longlong_as_double(0x7ff8000000000000LL);
+      table[(size_t)PD_NTAB * n_entry + j] = code;
+    }
+  }
+  if (n >= n_entry) return;
+  for (int t = 0; t < PD_NTAB; ++t) {
+    const double rate = (double)n * L.U.p[pd_tab_param[t]];
+    double code = 0.0;
+    if (rate > 0) {
+      const double mean = rate * dt;
+      if (mean > 0.0) code = pd_tau_code(mean);
+      else if (!(mean == 0.0)) code = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    table[(size_t)t * n_entry + n] = code;
+  }
+}
+
 /* a finished draw is parked in the list cell of its code; with 32-bit counts it saturates at
  * 2^31 - 1, which changes nothing: a clamp brings it down to a count anyway and an unclamped
  * gain of that size raises PD_ERR_COUNT_RANGE either way */
@@ -105,6 +148,8 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   for (int it = 1; it < a.n_time; ++it) {
     if (active) {
       const double dt = a.target[it] - a.target[it - 1];    /* :820 */
+      const bool use_table = (PD_NTAB + PD_NUNI) > 0 && a.code_table != 0 &&
+                             dt == a.code_table_dt;
 
       /* ---- 1. rate pass (:822-824): start-of-step counts as doubles; every rate of this step
        * is formed from them, the live counts only enter through the clamps (:833-841) */
@@ -114,25 +159,42 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
       pd_event_mults(yd, U, pm, time, (const double *)0, mult);
       pd_mask live = 0;
       int end = 0;                                          /* append cursor (list offset) */
+#define PD_TAU_APPEND(e, code)                                                       \
+  { s_list[end] = (code); end += PD_BLOCK; live |= (pd_mask)1 << e; }
 #define PD_TAU_CODE(e, mean)                                                         \
-  if (mean > 0.0) {                                                                  \
-    double code;                                                                     \
-    if (mean >= 10.0) code = -mean; else code = pd_exp_nonpos(-mean);                \
-    s_list[end] = code;                                                              \
-    end += PD_BLOCK;                                                                 \
-    live |= (pd_mask)1 << e;                                                         \
-  } else if (!(mean == 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }
+  if (mean > 0.0) PD_TAU_APPEND(e, pd_tau_code(mean))                                \
+  else if (!(mean == 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }
+#define PD_TAU_COMPUTED(e, rate)                                                     \
+  { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
+/* a row of the form count * uniform parameter: looked up by count when the launch has a table */
+#define PD_TAU_FIXED(e, from, rate)                                                  \
+  if (PD_ROW_TAB_##e >= 0 && use_table && y[from] < (pd_count)a.code_table_n) {      \
+    const double code = a.code_table[(PD_ROW_TAB_##e < 0 ? 0 : PD_ROW_TAB_##e) *     \
+                                     a.code_table_n + (int)y[from]];                 \
+    if (code != 0.0) {                                                               \
+      if (code != code) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
+      else PD_TAU_APPEND(e, code)                                                    \
+    }                                                                                \
+  } else PD_TAU_COMPUTED(e, rate)
 #define PD_TAU_ENTRY(e, to, is_int, rate)                                            \
-  { const double mean = rate * dt; PD_TAU_CODE(e, mean) }
-#define PD_TAU_TRANSFER(e, from, to, rate)                                           \
-  { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
-#define PD_TAU_DEATH(e, from, rate)                                                  \
-  { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
+  if (PD_ROW_UNI_##e >= 0 && use_table) {                                            \
+    const double code = a.code_table[PD_NTAB * a.code_table_n +                      \
+                                     (PD_ROW_UNI_##e < 0 ? 0 : PD_ROW_UNI_##e)];     \
+    if (code != 0.0) {                                                               \
+      if (code != code) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
+      else PD_TAU_APPEND(e, code)                                                    \
+    }                                                                                \
+  } else { const double mean = rate * dt; PD_TAU_CODE(e, mean) }
+#define PD_TAU_TRANSFER(e, from, to, rate) PD_TAU_FIXED(e, from, rate)
+#define PD_TAU_DEATH(e, from, rate) PD_TAU_FIXED(e, from, rate)
       PD_FOR_EACH_LIVE_ROW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
 #undef PD_TAU_ENTRY
 #undef PD_TAU_TRANSFER
 #undef PD_TAU_DEATH
+#undef PD_TAU_FIXED
+#undef PD_TAU_COMPUTED
 #undef PD_TAU_CODE
+#undef PD_TAU_APPEND
 
       /* ---- 2. draw loop.  Lane state: list cursor, the current event's code, its running
        * product and count */

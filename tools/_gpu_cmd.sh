@@ -1,1 +1,2 @@
-ncu --set full --import-source on --clock-control none -k pd_gillespie_kernel -c 1 -o gpurun_out/gillespie_r1b python tools/run_one.py cts final 32 256 4 262144 200 1 > gpurun_out/ncu_g.log 2>&1; tail -1 gpurun_out/ncu_g.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for cfg in "final 256 4" "stats 256 4"; do set -- $cfg; python tools/run_one.py dts $1 32 $2 $3 1048576 200 2>&1 | tail -1; done
