@@ -34,15 +34,21 @@ T_END = 1000
 QUANTILES = [0.025, 0.25, 0.5, 0.75, 0.975]
 HIST_BINS = 2048
 HIST_MAX = 2047          # strains counts stay well below 2048 (S ~ 1000-2000): width-1 bins
-# Roofline unit costs of pd_tau_leap_kernel on this workload (measured with
-# ncu, profiles/r1_tau_leap_stats_bench_ncu_summary.txt): the kernel is bound by SM instruction issue,
-# so the work unit is the thread-instruction.
-#   USEFUL_INST_PER_MEMBER_STEP: predicated-on thread instructions one member-step needs
-#   (smsp__thread_inst_executed_pred_on.sum / member-steps of the captured launch);
-#   HBM bytes per member-step: the streaming-statistics mode reads y0 once and writes nothing per
-#   step; DRAM_BYTES_PER_MEMBER_STEP is dram__bytes_read+write of the same capture per member-step.
-USEFUL_INST_PER_MEMBER_STEP = 1332.0   # thread_inst_executed_true 2.6635e12 / 2e9 member-steps
-DRAM_BYTES_PER_MEMBER_STEP = 0.0042    # dram__bytes_read 8.37 MB + write 512 B over 2e9 member-steps
+# Roofline unit costs of pd_tau_leap_kernel on this workload.  The kernel
+# is bound by SM instruction issue, so the work unit is the thread-operation.
+#   ALGORITHMIC_OPS_PER_MEMBER_STEP: SURVEY.md 8(d)'s per-unit figure for the strains model --
+#   S Poisson draws x (one exp ~ 25-30 fp64 ops + (lambda + 1) uniforms x ~45 int32 Philox ops)
+#   ~ 300 fp64 + ~1000 int32 operations per member-step.  It does not depend on this
+#   implementation (which needs fewer: see USEFUL_INST).
+#   USEFUL_INST_PER_MEMBER_STEP: predicated-on thread instructions the current kernel executes
+#   per member-step (ncu thread_inst_executed_true / member-steps of the captured launch,
+#   profiles/r1_tau_leap_stats_bench_ncu_summary.txt): 2.326e12 / 2e9.
+#   DRAM_BYTES_PER_MEMBER_STEP: dram__bytes_read + write of the same capture per member-step
+#   (8.36 MB over 2e9 member-steps); the streaming-statistics mode reads y0 once and writes
+#   nothing per step.
+ALGORITHMIC_OPS_PER_MEMBER_STEP = 1300.0
+USEFUL_INST_PER_MEMBER_STEP = 1163.0
+DRAM_BYTES_PER_MEMBER_STEP = 0.0042
 SM_COUNT = 148
 LANES_PER_SM_PER_CLK = 128          # 4 schedulers x 1 warp instruction x 32 lanes
 
@@ -312,18 +318,21 @@ def run_gpu_arm(args):
         member_steps = float(M) * steps_per_member
         sm_mhz = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz') or 1965.0
         issue_peak = SM_COUNT * LANES_PER_SM_PER_CLK * sm_mhz * 1e6 / 1e9      # G thread-inst/s
-        achieved = USEFUL_INST_PER_MEMBER_STEP * member_steps / (k_ms * 1e-3) / 1e9
+        achieved = ALGORITHMIC_OPS_PER_MEMBER_STEP * member_steps / (k_ms * 1e-3) / 1e9
+        useful = USEFUL_INST_PER_MEMBER_STEP * member_steps / (k_ms * 1e-3) / 1e9
         hbm_peak = peaks.get('hbm_gbs')
         roofline = {
             'bound': 'issue', 'kernel': 'pd_tau_leap_kernel',
-            'achieved': achieved, 'peak': issue_peak, 'unit': 'G thread-inst/s',
+            'achieved': achieved, 'peak': issue_peak, 'unit': 'G thread-op/s',
             'frac': achieved / issue_peak,
+            'frac_executed_useful': useful / issue_peak,
             'traffic': (DRAM_BYTES_PER_MEMBER_STEP * member_steps
                         if DRAM_BYTES_PER_MEMBER_STEP is not None else None),
             'peak_source': '%d SMs x %d lanes/clk x %.0f MHz (median SM clock sampled during the '
                            'timed region)' % (SM_COUNT, LANES_PER_SM_PER_CLK, sm_mhz),
-            'per_unit': '%.0f useful thread-instructions per member-step (ncu, profiles/)'
-                        % USEFUL_INST_PER_MEMBER_STEP,
+            'per_unit': '%.0f algorithmic operations per member-step (SURVEY.md 8d); the kernel '
+                        'executes %.0f useful thread-instructions per member-step (ncu, profiles/)'
+                        % (ALGORITHMIC_OPS_PER_MEMBER_STEP, USEFUL_INST_PER_MEMBER_STEP),
             'kernel_ms': k_ms, 'share_of_step': k_ms / float(np.mean(step_ms)),
             'pipe_peaks_gops': {'int32_imad_lop3': int_peak, 'fp64_dmul_dadd': fp64_peak},
             'hbm': {'algorithmic_bytes_per_member_step': 0.0,
