@@ -324,12 +324,19 @@ def integrate_single(model, y, method, is_continue):
     """One member, full trajectory: the body of ``BaseModel.integrate``."""
     cm = compiler.compile_model(model, method, is_continue=is_continue)
     seed = model.seed if model.seed is not None else random.getrandbits(63)
+    # With a fixed model.seed every integrate(is_continue=True) segment gets its OWN Philox
+    # stream -- stream id = number of the segment -- instead of replaying the first one: the
+    # reference's global generators simply keep going across segments (examples/mix_model.py:
+    # 123-134), so its segments are independent.
+    segment = getattr(model, '_segment', 0) + 1 if is_continue else 0
+    model._segment = segment
     res = run_compiled(model, cm, method, y, model.target_times, 1, output='full', seed=seed,
-                       device=model.device)
+                       member_offset=segment, device=model.device)
     raise_device_error(res.info, method)
     info = dict(res.info)
     info['soln'] = numpy.ascontiguousarray(res.soln[:, :, 0])
     info['seed'] = seed
+    info['stream'] = segment
     return info
 
 

@@ -287,6 +287,31 @@ def test_dropin_integrate_stochastic_single_member():
         assert 'prevalence' in m.var_labels
 
 
+def test_continued_stochastic_segments_do_not_replay_the_same_stream():
+    # with a fixed model.seed, integrate(is_continue=True) must not restart the Philox stream:
+    # two consecutive segments from the SAME state with the same grid would otherwise repeat
+    def two_segments():
+        m = helpers.make_model('sir', params={'population': 400, 'start_infectious': 40.})
+        m.seed = 77
+        m.make_times(0, 5, 1)
+        m.integrate('continuous_time_stochastic')
+        first = m.soln_array.copy()
+        m.make_times(5, 10, 1)
+        m.integrate('continuous_time_stochastic', is_continue=True)
+        return first, m.soln_array[5:], m.last_run_info['stream']
+    a_first, a_second, stream = two_segments()
+    b_first, b_second, _ = two_segments()
+    assert stream == 1
+    assert np.array_equal(a_first, b_first) and np.array_equal(a_second, b_second)   # reproducible
+    # the continued segment is what the oracle produces from stream 1 of the same seed
+    m = helpers.make_model('sir', params={'population': 400, 'start_infectious': 40.})
+    m.make_times(5, 10, 1)
+    om = oracle.OracleModel(helpers.compiled(m, 'continuous_time_stochastic'))
+    want, _, err = om.gillespie([float(v) for v in a_first[-1]], m.target_times,
+                                oracle.Rng('philox', seed=77, member=1))
+    assert err == 0 and np.array_equal(want, a_second)
+
+
 def test_mix_model_hybrid_switching_runs():
     # examples/mix_model.py:107-136: per-day switching between CTS and explicit via is_continue
     m = helpers.make_model('mix', params={'start_population': 100})
