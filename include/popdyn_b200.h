@@ -93,6 +93,10 @@ typedef struct {
   const int32_t *hist_shift;      /* [C] HOST: bin = min(count >> shift, bins - 1)            */
   int32_t hist_bins, n_hist_row;
   void *stream;                   /* cudaStream_t or NULL                                     */
+  const uint8_t *mask;            /* [M] or NULL: only members with mask[m] == mask_value are
+                                     integrated, the outputs of the others are left untouched
+                                     (PD_FULL / PD_FINAL only)                                */
+  int32_t mask_value, reserved;
 } pd_stoch_run;
 
 typedef struct {
@@ -108,6 +112,8 @@ typedef struct {
   double *soln;                   /* PD_FULL  [T][C][M]                                       */
   double *final_state;            /* PD_FINAL [C][M]                                          */
   void *stream;
+  const uint8_t *mask;            /* as in pd_stoch_run                                       */
+  int32_t mask_value, reserved;
 } pd_explicit_run;
 
 /* The diagnostics pass over stored trajectories (model built with method PD_DIAGNOSTICS, the

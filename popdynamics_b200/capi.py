@@ -75,7 +75,8 @@ class StochRun(C.Structure):
                 ('uniforms', C.c_void_p), ('n_uniform', C.c_int64),
                 ('soln', C.c_void_p), ('final_state', C.c_void_p), ('moments', C.c_void_p),
                 ('hist', C.c_void_p), ('hist_row', C.c_void_p), ('hist_shift', C.c_void_p),
-                ('hist_bins', C.c_int32), ('n_hist_row', C.c_int32), ('stream', C.c_void_p)]
+                ('hist_bins', C.c_int32), ('n_hist_row', C.c_int32), ('stream', C.c_void_p),
+                ('mask', C.c_void_p), ('mask_value', C.c_int32), ('reserved', C.c_int32)]
 
 
 class ExplicitRun(C.Structure):
@@ -84,7 +85,8 @@ class ExplicitRun(C.Structure):
                 ('uniform_params', C.c_void_p), ('member_params', C.c_void_p),
                 ('n_sub', C.c_void_p), ('dt', C.c_void_p), ('t_eval', C.c_void_p),
                 ('scaleup_table', C.c_void_p), ('n_steps', C.c_int64),
-                ('soln', C.c_void_p), ('final_state', C.c_void_p), ('stream', C.c_void_p)]
+                ('soln', C.c_void_p), ('final_state', C.c_void_p), ('stream', C.c_void_p),
+                ('mask', C.c_void_p), ('mask_value', C.c_int32), ('reserved', C.c_int32)]
 
 
 class DiagRun(C.Structure):

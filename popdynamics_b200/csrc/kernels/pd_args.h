@@ -56,8 +56,11 @@ typedef struct {
                                   by pd_tau_table_kernel when every step has the same dt; NULL
                                   otherwise                                                      */
   double code_table_dt;        /* the dt the table was built for                                 */
+  const unsigned char *mask;   /* [M] or NULL: only members with mask[m] == mask_value run, the
+                                  others are left untouched (hybrid switching, one launch per
+                                  integrator over the same state)                                */
   int code_table_n;
-  int pad1;
+  int mask_value;
 } PdStochArgs;
 
 /* Streaming statistics are reduced once per EPOCH of PD_EPOCH recorded target times: a lane keeps
@@ -92,8 +95,9 @@ typedef struct {
   double *soln;                /* FULL  [T][C][M]                                                */
   double *final_state;         /* FINAL [C][M]                                                   */
   int *err;
+  const unsigned char *mask;   /* [M] or NULL: only members with mask[m] == mask_value run       */
   int n_time;
-  int pad;
+  int mask_value;
 } PdExplicitArgs;
 
 typedef struct {

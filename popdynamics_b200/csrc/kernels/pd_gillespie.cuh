@@ -133,7 +133,8 @@ extern "C" __global__ void __launch_bounds__(PD_BLOCK, PD_MIN_BLOCKS)
 pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
   const PdStochArgs &a = L.a;
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + threadIdx.x;
-  const bool active = m < a.n_member;
+  const bool active = m < a.n_member &&
+                      (!a.mask || a.mask[m < a.n_member ? m : 0] == (unsigned char)a.mask_value);
   const pd_i64 M = a.n_member;
 
 #if PD_OUT_MODE == PD_OUT_STATS

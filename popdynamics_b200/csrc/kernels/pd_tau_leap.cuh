@@ -109,7 +109,8 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   const PdUniform &U = L.U;
   const int tid = threadIdx.x;
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + tid;
-  const bool active = m < a.n_member;
+  const bool active = m < a.n_member &&
+                      (!a.mask || a.mask[m < a.n_member ? m : 0] == (unsigned char)a.mask_value);
   const pd_i64 M = a.n_member;
 
   extern __shared__ double s_dyn[];
@@ -311,9 +312,9 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
     if (!bad && rng.exhausted) bad = PD_ERR_STREAM;
     if (bad) pd_raise(a.err, bad, a.member0 + m, 0);
   }
-  if (tid == 0 && a.n_steps) {
-    const pd_i64 first = (pd_i64)blockIdx.x * PD_BLOCK;
-    const pd_i64 here = (M - first < PD_BLOCK) ? (M - first) : PD_BLOCK;
-    atomicAdd(a.n_steps, (pd_u64)here * (pd_u64)(a.n_time - 1));
+  if (a.n_steps) {
+    const pd_u32 lanes = __popc(__ballot_sync(PD_FULL_MASK, active));
+    if ((tid & 31) == 0 && lanes)
+      atomicAdd(a.n_steps, (pd_u64)lanes * (pd_u64)(a.n_time - 1));
   }
 }

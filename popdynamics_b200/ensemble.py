@@ -178,12 +178,13 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
                  member_offset=0, uniforms=None, device=0, count_bits=64, block=256,
                  hist_bins=0, hist_max=None, hist_times=None, out=None, moments=None,
                  hist=None, member_params=None, y0=None, stream=None, min_dt=None,
-                 min_blocks=0, statistics='host'):
+                 min_blocks=0, statistics='host', mask=None, mask_value=0):
     """Launch one compiled model.  Returns an EnsembleResult.  ``out`` / ``moments`` / ``hist`` /
     ``member_params`` / ``y0`` let the caller supply resident (torch CUDA) buffers.
     ``statistics='device'`` keeps the streaming-statistics accumulators (moments, histograms)
     in HBM as torch tensors created here: only what ``mean`` / ``var`` / ``quantiles`` return
-    ever crosses PCIe, not the histograms themselves."""
+    ever crosses PCIe, not the histograms themselves.  ``mask`` ([M] uint8) restricts the launch to
+    the members with ``mask[m] == mask_value``; the outputs of the others are left untouched."""
     method_code = capi.METHOD_CODES[method]
     out_code = capi.OUTPUT_CODES[output]
     rng_code = capi.INJECT if uniforms is not None else capi.PHILOX
@@ -295,6 +296,9 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
             run.hist_shift = capi.address(shift)
             run.hist_bins, run.n_hist_row = hist_bins, len(rows)
     run.stream = stream
+    if mask is not None:
+        run.mask, run.mask_value = capi.address(mask), int(mask_value)
+        keep.append(mask)
 
     result = capi.run(kernel, run)
     res.info.update(result.as_dict())
@@ -379,6 +383,85 @@ def integrate_ensemble(model, method='explicit', n_members=None, output='full', 
                        statistics=statistics, **buffers)
     if check:
         raise_device_error(res.info, method)
+    return res
+
+
+def integrate_hybrid(model, segments, n_members, cutoff, seed=0, member_offset=0, device=None,
+                     stochastic_method='continuous_time_stochastic', output='final',
+                     count_bits=64, block=256):
+    """
+    Per-segment switching between a stochastic integrator and explicit Euler for every member of
+    an ensemble -- the loop of /root/reference/examples/mix_model.py:107-136 over
+    ``integrate(method, is_continue=True)`` (basepop.py:874-876, 894-899), batched:
+
+      * ``segments`` is a list of ``make_times`` argument tuples, one per segment;
+      * the first segment is stochastic (mix_model.py:118-121); before every later segment a
+        member whose smallest compartment exceeds ``cutoff`` switches to 'explicit', the others
+        to ``stochastic_method`` (:126-133);
+      * a segment starts from the last row of the previous one; entering a stochastic segment
+        truncates the state with ``int()`` (basepop.py:747-748); explicit segments are continued
+        runs, where Python's ``sum`` folds plainly over ``numpy.float64`` (SURVEY.md 3.6);
+      * every segment restarts its clock at its first target time, as ``integrate`` does.
+
+    Both integrators are launched over the same state buffer with complementary member masks.
+    Philox streams: stream id = segment << 40 | global member id, so segments are independent
+    and the result does not depend on sharding.  Returns an EnsembleResult with ``final``
+    [C][M] and, for ``output='full'``, ``soln`` [T][C][M] / ``times`` of the concatenated grid,
+    plus ``modes`` [n_segments][M] (1 = explicit).  Buffers are torch CUDA tensors."""
+    import torch
+    if output not in ('final', 'full'):
+        raise ValueError("integrate_hybrid supports output='final' or 'full'")
+    device = model.device if device is None else device
+    cuda = torch.device('cuda', device)
+    M = int(n_members)
+    model.check_flow_transfers()
+    y = model.get_init_list()
+    init, per_member = _initial_state(model, y, M)
+    C = len(model.labels)
+    state = torch.empty((C, M), dtype=torch.float64, device=cuda)
+    state[:] = torch.from_numpy(numpy.ascontiguousarray(init)).to(cuda).reshape(C, -1)
+    res = EnsembleResult()
+    res.method, res.output, res.labels = 'hybrid', output, list(model.labels)
+    res.n_members, res.member_offset, res.seed, res.device = M, member_offset, seed, device
+    rows, times, modes = [], [], []
+    member_blocks = {}
+    for k, seg in enumerate(segments):
+        model.make_times(*seg)
+        tt = list(model.target_times)
+        T = len(tt)
+        if k == 0:
+            explicit = torch.zeros(M, dtype=torch.uint8, device=cuda)
+        else:
+            explicit = (state.min(dim=0).values > cutoff).to(torch.uint8)
+        modes.append(explicit)
+        n_explicit = int(explicit.sum().item())
+        buf = torch.empty((T, C, M), dtype=torch.float64, device=cuda) if output == 'full' else state
+        for method, value, count in ((stochastic_method, 0, M - n_explicit),
+                                     ('explicit', 1, n_explicit)):
+            if not count:
+                continue
+            cm = compiler.compile_model(model, method, is_continue=(k > 0))
+            if method not in member_blocks:        # slot order depends on the trace
+                block_ = _member_param_block(cm, M)
+                member_blocks[method] = None if block_ is None else \
+                    torch.from_numpy(block_).to(cuda)
+            part = run_compiled(model, cm, method, y, tt, M, output=output, seed=seed,
+                                member_offset=member_offset + (k << 40), device=device,
+                                count_bits=count_bits, block=block, y0=state, out=buf,
+                                member_params=member_blocks[method], mask=explicit,
+                                mask_value=value)
+            raise_device_error(part.info, method)
+            res.info.setdefault('launches', []).append(
+                dict(segment=k, method=method, members=count, kernel_ms=part.info['kernel_ms']))
+        if output == 'full':
+            rows.append(buf if k == 0 else buf[1:])
+            times.extend(tt if k == 0 else tt[1:])
+            state = buf[-1].clone()
+    res.final = state
+    res.modes = torch.stack(modes)
+    if output == 'full':
+        res.soln = torch.cat(rows, dim=0)
+        res.times = numpy.asarray([float(t) for t in times])
     return res
 
 

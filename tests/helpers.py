@@ -71,3 +71,32 @@ def inverted_cdf_quantiles(samples, q):
         rank = max(1, int(np.ceil(qq * n)))
         out.append(s[rank - 1])
     return np.array(out)
+
+
+def oracle_hybrid(make_model_fn, segments, cutoff, rng_for_segment,
+                  stochastic_method='continuous_time_stochastic'):
+    """The loop of examples/mix_model.py:107-136 over the oracle: first segment stochastic, then
+    per segment explicit when min(compartments) > cutoff; every segment is a continued run
+    starting from the last row.  ``rng_for_segment(k)`` gives the uniform source of segment k.
+    Returns (soln rows of the concatenated grid, list of modes)."""
+    m = make_model_fn()
+    rows, modes, state = None, [], None
+    for k, seg in enumerate(segments):
+        m.make_times(*seg)
+        if k == 0:
+            state = [float(v) for v in m.get_init_list()]
+            method = stochastic_method
+        else:
+            method = 'explicit' if min(state) > cutoff else stochastic_method
+        modes.append(method)
+        cm = compiled(m, method, is_continue=(k > 0))
+        om = oracle.OracleModel(cm)
+        if method == 'explicit':
+            soln, _, err = om.explicit(state, m.target_times)
+        else:
+            fn = om.gillespie if method == 'continuous_time_stochastic' else om.tau_leap
+            soln, _, err = fn(state, m.target_times, rng_for_segment(k))
+        assert err == 0
+        rows = soln if rows is None else np.concatenate([rows, soln[1:]], 0)
+        state = [float(v) for v in soln[-1]]
+    return rows, modes

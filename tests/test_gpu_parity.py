@@ -330,6 +330,26 @@ def test_mix_model_hybrid_switching_runs():
     assert np.all(m.soln_array >= 0)
 
 
+def test_hybrid_switching_ensemble_matches_the_oracle_loop_per_member():
+    # the mix_model.py loop batched -- both integrators launched over the same
+    # state with complementary member masks, stream id = segment << 40 | member
+    n, seed, cutoff = 300, 17, 3
+    segments = [(d, d + 1, 0.2) for d in range(14)]
+    m = helpers.make_model('mix', params={'start_population': 100})
+    res = ensemble.integrate_hybrid(m, segments, n, cutoff, seed=seed, output='full')
+    soln = res.soln.cpu().numpy()
+    modes = res.modes.cpu().numpy()
+    assert 0 < modes[1:].sum() < modes[1:].size            # both integrators were exercised
+    for i in (0, 1, 150, n - 1):
+        rows, want_modes = helpers.oracle_hybrid(
+            lambda: helpers.make_model('mix', params={'start_population': 100}), segments, cutoff,
+            lambda k: oracle.Rng('philox', seed=seed, member=(k << 40) + i))
+        assert [int(v) for v in modes[:, i]] == [int(w == 'explicit') for w in want_modes]
+        assert np.array_equal(soln[:, :, i], rows), 'member %d' % i
+    final = ensemble.integrate_hybrid(m, segments, n, cutoff, seed=seed, output='final').final
+    assert np.array_equal(final.cpu().numpy(), soln[-1])
+
+
 # ------------------------------------------------------------------------------- statistics
 @pytest.mark.parametrize('method', ['discrete_time_stochastic', 'continuous_time_stochastic'])
 def test_streaming_statistics_equal_numpy_over_full_trajectories(method):

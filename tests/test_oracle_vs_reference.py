@@ -99,6 +99,32 @@ def test_tb_with_scaleups_in_the_stochastic_loops_matches_the_reference(method, 
     assert err == 0 and np.array_equal(soln, theirs.soln_array)
 
 
+def test_hybrid_switching_loop_of_mix_model_matches_the_reference():
+    # examples/mix_model.py:107-136, run on the unmodified reference with both global generators
+    # seeded; the oracle walks the same loop with ONE MT19937 stream shared by all segments
+    Sir = reference.example_classes('mix_model.py')['SirModel']
+    reference.seed_all(13)
+    theirs = Sir({'start_population': 100})
+    theirs.make_times(0, 1, 0.2)
+    theirs.integrate(method='continuous_time_stochastic')
+    segments, n_explicit = [(0, 1, 0.2)], 0
+    day = 1
+    while day < 30:
+        method = 'explicit' if min(theirs.compartments.values()) > 3 \
+            else 'continuous_time_stochastic'
+        n_explicit += method == 'explicit'
+        theirs.make_times(day, day + 1, 0.2)
+        theirs.integrate(method=method, is_continue=True)
+        segments.append((day, day + 1, 0.2))
+        day += 1
+    shared = oracle.Rng('python', 13)
+    rows, modes = helpers.oracle_hybrid(
+        lambda: helpers.make_model('mix', params={'start_population': 100}), segments, 3,
+        lambda k: shared)
+    assert 0 < n_explicit < 29 and modes.count('explicit') == n_explicit
+    assert np.array_equal(rows, theirs.soln_array)
+
+
 def test_golden_file_is_current(golden):
     # the committed fixtures are what the reference produces today
     m = reference.example_classes('sir_model.py')['SirModel']()
