@@ -53,6 +53,12 @@ SM_COUNT = 148
 LANES_PER_SM_PER_CLK = 128          # 4 schedulers x 1 warp instruction x 32 lanes
 
 
+def workload_name(members_per_gpu):
+    return ('stochastic_strains_model DTS (clamped Poisson tau-leap), make_times(0,1000,1), C=5, '
+            '%d members per GPU, streaming mean/var + %d-bin histograms -> 5 quantiles per (t,c)'
+            % (members_per_gpu, HIST_BINS))
+
+
 def make_model():
     from examples import models
     model = models.StrainsModel()
@@ -173,9 +179,10 @@ def run_reference_arm(args):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'int64+f64', 'data': 'synthetic',
-        'config': {'workload': 'stochastic_strains_model DTS, make_times(0,1000,1), C=5, '
-                               'bounded sample of the 10^7-member ensemble',
-                   'members_per_step': n_member},
+        'config': {'workload': workload_name(args.members),
+                   'sample_members_per_step': n_member,
+                   'note': 'each step is a bounded sample of the workload: the oracle port runs '
+                           'sample_members_per_step members with streaming moments'},
         'cpu_baseline': {'value': value, 'unit': 'comp-steps/s', 'cores': cores, 'kind': 'port',
                          'sample': sample,
                          'note': 'C restatement of basepop.py:797-852 (oracle/popdyn_oracle.c); '
@@ -353,10 +360,7 @@ def run_gpu_arm(args):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'int%d+f64' % args.count_bits, 'data': 'synthetic',
             'members_per_sec': float(world) * M * args.steps / (total_ms * 1e-3),
-            'config': {'workload': 'stochastic_strains_model DTS (clamped Poisson tau-leap), '
-                                   'make_times(0,1000,1), C=5, %d members per GPU, streaming '
-                                   'mean/var + %d-bin histograms -> 5 quantiles per (t,c)'
-                                   % (M, HIST_BINS),
+            'config': {'workload': workload_name(M),
                        'members_per_gpu': M, 'steps_per_member': steps_per_member,
                        'parallelism': 'members sharded x%d, all-reduce of integer statistics'
                                       % world,
