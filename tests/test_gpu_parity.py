@@ -253,6 +253,42 @@ def test_native_philox_bit_exact_against_oracle(method, count_bits):
     assert np.array_equal(final.T, want['soln'][:, -1, :])
 
 
+def test_tau_leap_on_an_irregular_grid_with_repeated_and_decreasing_times():
+    # the code tables are built for the first dt only: other steps compute their codes; a
+    # repeated target time (dt = 0) draws nothing; a decreasing one gives negative Poisson means,
+    # which numpy rejects with ValueError
+    m = helpers.make_model('strains')
+    m.target_times = [0., 1., 2., 2.5, 2.5, 4., 4.25, 9., 10., 11.]
+    n, seed = 200, 21
+    for count_bits in (32, 64):
+        res = m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='full',
+                                   seed=seed, count_bits=count_bits)
+        om = oracle.OracleModel(helpers.compiled(m, 'discrete_time_stochastic'))
+        want = om.stochastic_batch('discrete_time_stochastic', n, m.get_init_list(),
+                                   m.target_times, seed)
+        assert want['err'] == 0
+        assert np.array_equal(np.transpose(res.soln, (2, 0, 1)), want['soln'])
+        assert np.array_equal(res.soln[3], res.soln[4])              # dt = 0: nothing happens
+    m.target_times = [0., 1., 0.5, 2.]
+    om = oracle.OracleModel(helpers.compiled(m, 'discrete_time_stochastic'))
+    assert om.stochastic_batch('discrete_time_stochastic', 4, m.get_init_list(), m.target_times,
+                               seed)['err'] == 2
+    with pytest.raises(ValueError, match='Poisson mean'):
+        m.integrate_ensemble('discrete_time_stochastic', n_members=4, output='final', seed=seed)
+    # without the tables the trajectories are the same (POPDYN_CODE_TABLE=0 is read per launch)
+    import os
+    m.target_times = [float(t) for t in range(40)]
+    with_tables = m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='final',
+                                       seed=seed).final
+    os.environ['POPDYN_CODE_TABLE'] = '0'
+    try:
+        without = m.integrate_ensemble('discrete_time_stochastic', n_members=n, output='final',
+                                       seed=seed).final
+    finally:
+        del os.environ['POPDYN_CODE_TABLE']
+    assert np.array_equal(with_tables, without)
+
+
 def test_shard_invariance_by_global_member_id():
     m = helpers.make_model('strains')
     m.make_times(0, 60, 1)
