@@ -347,9 +347,15 @@ def integrate_single(model, y, method, is_continue):
 def integrate_ensemble(model, method='explicit', n_members=None, output='full', seed=0,
                        member_offset=0, uniforms=None, device=None, count_bits=64, block=256,
                        hist_bins=0, hist_max=None, hist_times=None, check=True, min_blocks=0,
-                       statistics='host', **buffers):
+                       statistics='host', continue_from=None, **buffers):
     """
     Run ``n_members`` independent members of ``model`` (additive API, see module docstring).
+
+    ``continue_from=previous_result`` is ``integrate(..., is_continue=True)`` (basepop.py:874-876)
+    for an ensemble: every member starts from its last state in ``previous_result`` (``final``
+    or the last row of ``soln``), explicit runs take the continued-run arithmetic (plain ``sum``
+    fold), and the Philox streams move on to the next segment
+    (stream id = segment << 40 | global member id) instead of replaying the previous one.
 
     Per-member sweeps: give ``set_param`` / ``set_compartment`` 1-D arrays of length M.  Native
     Philox streams are keyed by ``(seed, member_offset + i)``: results do not depend on how the
@@ -363,7 +369,22 @@ def integrate_ensemble(model, method='explicit', n_members=None, output='full', 
     model.clear_solns()
     model.check_flow_transfers()
     y = model.get_init_list()
-    cm = compiler.compile_model(model, method)
+    segment = 0
+    if continue_from is not None:
+        prev = continue_from
+        state = prev.final if prev.final is not None else \
+            (prev.soln[-1] if prev.soln is not None else None)
+        if state is None:
+            raise ValueError("continue_from needs a result with output='final' or 'full'")
+        if _is_torch(state):
+            state = state.contiguous()
+        else:
+            state = numpy.ascontiguousarray(state)
+        buffers = dict(buffers, y0=state)
+        n_members = prev.n_members if n_members is None else n_members
+        segment = getattr(prev, 'segment', 0) + 1
+        member_offset = prev.member_offset
+    cm = compiler.compile_model(model, method, is_continue=continue_from is not None)
     implied = cm.n_members_implied()
     for v in y:
         if isinstance(v, numpy.ndarray):
@@ -377,10 +398,12 @@ def integrate_ensemble(model, method='explicit', n_members=None, output='full', 
                          % (n_members, implied))
     device = model.device if device is None else device
     res = run_compiled(model, cm, method, y, model.target_times, n_members, output=output,
-                       seed=seed, member_offset=member_offset, uniforms=uniforms, device=device,
+                       seed=seed, member_offset=member_offset + (segment << 40),
+                       uniforms=uniforms, device=device,
                        count_bits=count_bits, block=block, hist_bins=hist_bins,
                        hist_max=hist_max, hist_times=hist_times, min_blocks=min_blocks,
                        statistics=statistics, **buffers)
+    res.member_offset, res.segment = member_offset, segment
     if check:
         raise_device_error(res.info, method)
     return res

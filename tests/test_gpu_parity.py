@@ -348,6 +348,26 @@ def test_continued_stochastic_segments_do_not_replay_the_same_stream():
     assert err == 0 and np.array_equal(want, a_second)
 
 
+def test_ensemble_continue_from_is_is_continue_for_every_member():
+    n, seed = 120, 9
+    m = helpers.make_model('strains')
+    for method in ('discrete_time_stochastic', 'explicit'):
+        m.make_times(0, 30, 1)
+        first = m.integrate_ensemble(method, n_members=n, output='final', seed=seed)
+        m.make_times(30, 50, 1)
+        second = m.integrate_ensemble(method, output='full', seed=seed, continue_from=first)
+        assert second.segment == 1 and second.n_members == n
+        om = oracle.OracleModel(helpers.compiled(m, method, is_continue=True))
+        for i in (0, 60, n - 1):
+            start = [float(v) for v in first.final[:, i]]
+            if method == 'explicit':
+                want, _, err = om.explicit(start, m.target_times)
+            else:
+                want, _, err = om.tau_leap(start, m.target_times,
+                                           oracle.Rng('philox', seed=seed, member=(1 << 40) + i))
+            assert err == 0 and np.array_equal(second.soln[:, :, i], want)
+
+
 def test_mix_model_hybrid_switching_runs():
     # examples/mix_model.py:107-136: per-day switching between CTS and explicit via is_continue
     m = helpers.make_model('mix', params={'start_population': 100})
