@@ -374,7 +374,8 @@ def run_gpu_arm(args):
                                        % (cpu_members, cpu_dt)},
             'e2e': {'value': e2e_value, 'unit': 'comp-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps},
-            'gpu_launches': 2 * args.steps,
+            # per timed step: pd_tau_table_kernel, pd_tau_leap_kernel, pd_quantiles_kernel
+            'gpu_launches': 3 * args.steps,
             'clocks': clocks, 'wall_s': wall,
         }
         print(json.dumps(line))
