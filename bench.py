@@ -42,21 +42,21 @@ HIST_MAX = 2047          # strains counts stay well below 2048 (S ~ 1000-2000): 
 #   implementation (which needs fewer: see USEFUL_INST).
 #   USEFUL_INST_PER_MEMBER_STEP: predicated-on thread instructions the current kernel executes
 #   per member-step (ncu thread_inst_executed_true / member-steps of the captured launch,
-#   profiles/r1_tau_leap_stats_bench_ncu_summary.txt): 2.326e12 / 2e9.
+#   profiles/r1_tau_leap_stats_bench_ncu_summary.txt): 2.077e12 / 2e9.
 #   DRAM_BYTES_PER_MEMBER_STEP: dram__bytes_read + write of the same capture per member-step
-#   (8.36 MB over 2e9 member-steps); the streaming-statistics mode reads y0 once and writes
+#   (8.28 MB over 2e9 member-steps); the streaming-statistics mode reads y0 once and writes
 #   nothing per step.
 ALGORITHMIC_OPS_PER_MEMBER_STEP = 1300.0
-USEFUL_INST_PER_MEMBER_STEP = 1163.0
-DRAM_BYTES_PER_MEMBER_STEP = 0.0042
+USEFUL_INST_PER_MEMBER_STEP = 1039.0
+DRAM_BYTES_PER_MEMBER_STEP = 0.0041
 SM_COUNT = 148
 LANES_PER_SM_PER_CLK = 128          # 4 schedulers x 1 warp instruction x 32 lanes
 
 
 def workload_name(members_per_gpu):
     return ('stochastic_strains_model DTS (clamped Poisson tau-leap), make_times(0,1000,1), C=5, '
-            '%d members per GPU, streaming mean/var + %d-bin histograms -> 5 quantiles per (t,c)'
-            % (members_per_gpu, HIST_BINS))
+            '%d members per GPU, streaming %d-bin width-1 histograms -> exact mean/var + 5 '
+            'quantiles per (t,c)' % (members_per_gpu, HIST_BINS))
 
 
 def make_model():
@@ -237,11 +237,14 @@ def run_gpu_arm(args):
                                     device=local_rank, count_bits=args.count_bits,
                                     block=args.block, min_blocks=args.min_blocks,
                                     hist_bins=HIST_BINS, hist_max=HIST_MAX,
-                                    moments=moments, hist=hist)
+                                    moments=moments, hist=hist, moments_from=args.moments_from)
         ensemble.raise_device_error(res.info, 'discrete_time_stochastic')
         if world > 1:
-            dist.all_reduce(moments)
             dist.all_reduce(hist)
+            if args.moments_from == 'hist':
+                res.derive_moments()              # exact moments of the whole ensemble
+            else:
+                dist.all_reduce(moments)
         capi.hist_quantiles(hist, n_rows, C, HIST_BINS, hist_shift, QUANTILES, quant,
                             device=local_rank)
         return res
@@ -297,6 +300,7 @@ def run_gpu_arm(args):
                                        seed=seed, member_offset=start, device=local_rank,
                                        count_bits=args.count_bits, block=args.block,
                                        min_blocks=args.min_blocks, statistics='device',
+                                       moments_from=args.moments_from,
                                        hist_bins=HIST_BINS, hist_max=HIST_MAX)
         if world > 1:
             distributed.allreduce_stats(res, device=dev)
@@ -374,8 +378,9 @@ def run_gpu_arm(args):
                                        % (cpu_members, cpu_dt)},
             'e2e': {'value': e2e_value, 'unit': 'comp-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps},
-            # per timed step: pd_tau_table_kernel, pd_tau_leap_kernel, pd_quantiles_kernel
-            'gpu_launches': 3 * args.steps,
+            # per timed step: pd_tau_table_kernel, pd_tau_leap_kernel, pd_hist_moments_kernel,
+            # pd_quantiles_kernel
+            'gpu_launches': 4 * args.steps,
             'clocks': clocks, 'wall_s': wall,
         }
         print(json.dumps(line))
@@ -394,6 +399,9 @@ def main():
                     help='width of the integer counts (32: overflow raises the device error flag)')
     ap.add_argument('--min-blocks', type=int, default=4, help='__launch_bounds__ resident-block cap')
     ap.add_argument('--block', type=int, default=256)
+    ap.add_argument('--moments-from', default='hist', choices=['hist', 'kernel'],
+                    help="'hist': exact moments derived from the width-1 histograms after the "
+                         "launch; 'kernel': reduced inside the integrator kernel")
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     args = ap.parse_args()
     if args.impl == 'reference':

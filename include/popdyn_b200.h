@@ -60,7 +60,13 @@ typedef struct {
   int32_t n_comp, n_param, n_member_param, n_scaleup, n_flow; /* must match the model header  */
   int32_t min_blocks;     /* __launch_bounds__ second argument: resident blocks per SM the
                              register allocation must allow (0 -> 1, i.e. no cap)             */
+  int32_t flags;          /* PD_FLAG_* bits                                                   */
+  int32_t reserved;
 } pd_model_desc;
+
+#define PD_FLAG_MEMBER_MASK 1   /* the kernel honours pd_*_run.mask (a separate specialisation:
+                                   testing for a mask in the general kernel costs 6 % of the
+                                   tau-leap step)                                              */
 
 typedef struct {
   double kernel_ms;       /* device time of the integrator kernel (CUDA events)               */
@@ -96,7 +102,11 @@ typedef struct {
   const uint8_t *mask;            /* [M] or NULL: only members with mask[m] == mask_value are
                                      integrated, the outputs of the others are left untouched
                                      (PD_FULL / PD_FINAL only)                                */
-  int32_t mask_value, reserved;
+  int32_t mask_value;
+  int32_t moments_from_hist;      /* 1: skip the in-kernel moment reduction; the caller runs
+                                     pd_hist_moments on the (lossless) histograms afterwards:
+                                     needs hist at every target time with hist_shift == 0; a
+                                     count in the last bin raises the device error flag         */
 } pd_stoch_run;
 
 typedef struct {
@@ -168,6 +178,9 @@ int pd_run_diagnostics(pd_model *m, const pd_diag_run *run, pd_run_result *res);
 /* Quantiles from (all-reduced) histograms: for every (row, c) and every q the smallest bin b with
  * cumulative count >= q * total (inverted CDF); value = b << shift[c].  hist / out may be host
  * or device.  out: [n_row][C][n_q] int64.                                                    */
+/* moments [n_row][C][2] = (sum x, sum x^2) derived from width-1 histograms (overwritten) */
+int pd_hist_moments(const uint32_t *hist, int32_t n_row, int32_t n_comp, int32_t n_bins,
+                    uint64_t *moments, int32_t device, void *stream);
 int pd_hist_quantiles(const uint32_t *hist, int32_t n_row, int32_t n_comp, int32_t n_bins,
                       const int32_t *hist_shift, const double *q, int32_t n_q, int64_t *out,
                       int32_t device, void *stream);

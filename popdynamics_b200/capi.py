@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     'pd_version', 'pd_last_error', 'pd_device_count', 'pd_struct_size', 'pd_model_create', 'pd_model_destroy',
     'pd_model_cubin_size', 'pd_model_cubin_copy', 'pd_explicit_schedule', 'pd_run_explicit',
     'pd_run_tau_leap', 'pd_run_gillespie', 'pd_run_diagnostics', 'pd_hist_quantiles',
-    'pd_philox_fill', 'pd_microbench')
+    'pd_hist_moments', 'pd_philox_fill', 'pd_microbench')
 
 
 class ExtensionMissing(RuntimeError):
@@ -53,7 +53,11 @@ class PopdynError(RuntimeError):
 class ModelDesc(C.Structure):
     _fields_ = [(name, C.c_int32) for name in
                 ('method', 'out_mode', 'rng_mode', 'count_bits', 'block', 'device', 'n_comp',
-                 'n_param', 'n_member_param', 'n_scaleup', 'n_flow', 'min_blocks')]
+                 'n_param', 'n_member_param', 'n_scaleup', 'n_flow', 'min_blocks', 'flags',
+                 'reserved')]
+
+
+FLAG_MEMBER_MASK = 1
 
 
 class RunResult(C.Structure):
@@ -76,7 +80,8 @@ class StochRun(C.Structure):
                 ('soln', C.c_void_p), ('final_state', C.c_void_p), ('moments', C.c_void_p),
                 ('hist', C.c_void_p), ('hist_row', C.c_void_p), ('hist_shift', C.c_void_p),
                 ('hist_bins', C.c_int32), ('n_hist_row', C.c_int32), ('stream', C.c_void_p),
-                ('mask', C.c_void_p), ('mask_value', C.c_int32), ('reserved', C.c_int32)]
+                ('mask', C.c_void_p), ('mask_value', C.c_int32),
+                ('moments_from_hist', C.c_int32)]
 
 
 class ExplicitRun(C.Structure):
@@ -130,6 +135,8 @@ def lib():
     L.pd_run_diagnostics.argtypes = [C.c_void_p, P(DiagRun), P(RunResult)]
     L.pd_hist_quantiles.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    L.pd_hist_moments.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_int32, C.c_void_p]
     L.pd_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64,
                                  C.c_int32, C.c_void_p]
     L.pd_microbench.argtypes = [C.c_int32, C.c_int32, P(C.c_double)]
@@ -165,9 +172,10 @@ class Model(object):
     """One NVRTC-specialised kernel (``pd_model``)."""
 
     def __init__(self, header_source, method, out_mode, rng_mode, device, n_comp, n_param,
-                 n_member_param, n_scaleup, n_flow, count_bits=64, block=256, min_blocks=0):
+                 n_member_param, n_scaleup, n_flow, count_bits=64, block=256, min_blocks=0,
+                 flags=0):
         self.desc = ModelDesc(method, out_mode, rng_mode, count_bits, block, device, n_comp,
-                              n_param, n_member_param, n_scaleup, n_flow, min_blocks)
+                              n_param, n_member_param, n_scaleup, n_flow, min_blocks, flags, 0)
         handle = C.c_void_p()
         check(lib().pd_model_create(header_source.encode(), C.byref(self.desc), C.byref(handle)))
         self.handle = handle
@@ -225,6 +233,13 @@ def hist_quantiles(hist, n_row, n_comp, n_bins, hist_shift, q, out, device=0, st
     check(lib().pd_hist_quantiles(address(hist), n_row, n_comp, n_bins, shift.ctypes.data,
                                   q.ctypes.data, len(q), address(out), device, stream))
     return out
+
+
+def hist_moments(hist, n_row, n_comp, n_bins, moments, device=0, stream=None):
+    """moments[n_row][n_comp][2] = (sum x, sum x^2) from width-1 histograms (overwritten)."""
+    check(lib().pd_hist_moments(address(hist), n_row, n_comp, n_bins, address(moments), device,
+                                stream))
+    return moments
 
 
 def philox_fill(out, n, n_member, member0, seed, device=0, stream=None):

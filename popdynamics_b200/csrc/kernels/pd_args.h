@@ -61,6 +61,11 @@ typedef struct {
                                   integrator over the same state)                                */
   int code_table_n;
   int mask_value;
+  int moments_from_hist;       /* 1: the caller derives the moments from the (lossless: shift 0,
+                                  every time recorded) histograms afterwards; the kernel skips
+                                  their reduction and raises PD_ERR_COUNT_RANGE for a count that
+                                  lands in the last (overflow) bin                               */
+  int pad2;
 } PdStochArgs;
 
 /* Streaming statistics are reduced once per EPOCH of PD_EPOCH recorded target times: a lane keeps

@@ -27,7 +27,9 @@ pd_explicit_kernel(const __grid_constant__ PdExplicitLaunch L) {
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + threadIdx.x;
   const pd_i64 M = a.n_member;
   if (m >= M) return;
-  if (a.mask && a.mask[m] != (unsigned char)a.mask_value) return;
+#if PD_USE_MASK
+  if (a.mask[m] != (unsigned char)a.mask_value) return;
+#endif
 
   double y[PD_C], f[PD_C], pm[PD_NPM_DIM];
   pm[0] = 0.0;

@@ -133,8 +133,11 @@ extern "C" __global__ void __launch_bounds__(PD_BLOCK, PD_MIN_BLOCKS)
 pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
   const PdStochArgs &a = L.a;
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + threadIdx.x;
-  const bool active = m < a.n_member &&
-                      (!a.mask || a.mask[m < a.n_member ? m : 0] == (unsigned char)a.mask_value);
+#if PD_USE_MASK
+  const bool active = m < a.n_member && a.mask[m < a.n_member ? m : 0] == (unsigned char)a.mask_value;
+#else
+  const bool active = m < a.n_member;
+#endif
   const pd_i64 M = a.n_member;
 
 #if PD_OUT_MODE == PD_OUT_STATS

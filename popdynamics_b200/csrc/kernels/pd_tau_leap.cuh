@@ -109,8 +109,11 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   const PdUniform &U = L.U;
   const int tid = threadIdx.x;
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + tid;
-  const bool active = m < a.n_member &&
-                      (!a.mask || a.mask[m < a.n_member ? m : 0] == (unsigned char)a.mask_value);
+#if PD_USE_MASK
+  const bool active = m < a.n_member && a.mask[m < a.n_member ? m : 0] == (unsigned char)a.mask_value;
+#else
+  const bool active = m < a.n_member;
+#endif
   const pd_i64 M = a.n_member;
 
   extern __shared__ double s_dyn[];

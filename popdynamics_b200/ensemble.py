@@ -26,14 +26,16 @@ _KERNEL_CACHE = {}
 _SCHEDULE_CACHE = {}
 
 
-def _kernel_for(cm, method, out_mode, rng_mode, device, count_bits, block, min_blocks=0):
+def _kernel_for(cm, method, out_mode, rng_mode, device, count_bits, block, min_blocks=0,
+                flags=0):
     source = cm.cuda_source()
-    key = (source, method, out_mode, rng_mode, device, count_bits, block, min_blocks)
+    key = (source, method, out_mode, rng_mode, device, count_bits, block, min_blocks, flags)
     kernel = _KERNEL_CACHE.get(key)
     if kernel is None:
         kernel = capi.Model(source, method, out_mode, rng_mode, device, cm.n_comp, cm.n_param,
                             len(cm.member_param_slots()), cm.n_su, cm.n_flow,
-                            count_bits=count_bits, block=block, min_blocks=min_blocks)
+                            count_bits=count_bits, block=block, min_blocks=min_blocks,
+                            flags=flags)
         _KERNEL_CACHE[key] = kernel
     return kernel
 
@@ -151,6 +153,13 @@ class EnsembleResult(object):
                             device=self.device)
         return out
 
+    def derive_moments(self):
+        """Exact moments from lossless histograms (``moments_from='hist'``); call again after the
+        histograms of several shards / ranks have been added up."""
+        capi.hist_moments(self.hist, len(self.hist_times), len(self.labels), self.hist_bins,
+                          self.moments, device=self.device)
+        return self.moments
+
     def trajectory(self, member):
         """(T, C) array of one member, the layout of the reference's ``soln_array``."""
         s = self.soln[:, :, member]
@@ -178,13 +187,16 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
                  member_offset=0, uniforms=None, device=0, count_bits=64, block=256,
                  hist_bins=0, hist_max=None, hist_times=None, out=None, moments=None,
                  hist=None, member_params=None, y0=None, stream=None, min_dt=None,
-                 min_blocks=0, statistics='host', mask=None, mask_value=0):
+                 min_blocks=0, statistics='host', mask=None, mask_value=0, moments_from='kernel'):
     """Launch one compiled model.  Returns an EnsembleResult.  ``out`` / ``moments`` / ``hist`` /
     ``member_params`` / ``y0`` let the caller supply resident (torch CUDA) buffers.
     ``statistics='device'`` keeps the streaming-statistics accumulators (moments, histograms)
     in HBM as torch tensors created here: only what ``mean`` / ``var`` / ``quantiles`` return
     ever crosses PCIe, not the histograms themselves.  ``mask`` ([M] uint8) restricts the launch to
-    the members with ``mask[m] == mask_value``; the outputs of the others are left untouched."""
+    the members with ``mask[m] == mask_value``; the outputs of the others are left untouched.
+    ``moments_from='hist'``: with lossless histograms (width-1 bins at every target time) the exact
+    moments are derived from them after the launch instead of being reduced inside the kernel; a
+    count that reaches the last bin raises the device error flag (choose a larger ``hist_max``)."""
     method_code = capi.METHOD_CODES[method]
     out_code = capi.OUTPUT_CODES[output]
     rng_code = capi.INJECT if uniforms is not None else capi.PHILOX
@@ -195,7 +207,7 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
         # kernel of a large flow table (TB: 20 rows, 84 registers) is better left uncapped
         min_blocks = max(1, 1024 // int(block))
     kernel = _kernel_for(cm, method_code, out_code, rng_code, device, count_bits, block,
-                         min_blocks)
+                         min_blocks, capi.FLAG_MEMBER_MASK if mask is not None else 0)
     C, T, M = cm.n_comp, len(target_times), int(n_members)
     tt = numpy.ascontiguousarray([float(t) for t in target_times], dtype=numpy.float64)
 
@@ -295,6 +307,13 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
             run.hist, run.hist_row = capi.address(res.hist), capi.address(row)
             run.hist_shift = capi.address(shift)
             run.hist_bins, run.n_hist_row = hist_bins, len(rows)
+        if moments_from == 'hist':
+            if not hist_bins or len(rows) != T or int(numpy.max(shift)) != 0:
+                raise ValueError("moments_from='hist' needs width-1 histogram bins at every "
+                                 "target time (hist_bins > hist_max, no hist_times)")
+            run.moments_from_hist = 1
+        elif moments_from != 'kernel':
+            raise ValueError("moments_from must be 'kernel' or 'hist'")
     run.stream = stream
     if mask is not None:
         run.mask, run.mask_value = capi.address(mask), int(mask_value)
@@ -302,6 +321,9 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
 
     result = capi.run(kernel, run)
     res.info.update(result.as_dict())
+    res.moments_from = moments_from if output == 'stats' else None
+    if res.moments_from == 'hist' and not result.err_code:
+        res.derive_moments()
     del keep
     return res
 
@@ -347,7 +369,7 @@ def integrate_single(model, y, method, is_continue):
 def integrate_ensemble(model, method='explicit', n_members=None, output='full', seed=0,
                        member_offset=0, uniforms=None, device=None, count_bits=64, block=256,
                        hist_bins=0, hist_max=None, hist_times=None, check=True, min_blocks=0,
-                       statistics='host', continue_from=None, **buffers):
+                       statistics='host', continue_from=None, moments_from='kernel', **buffers):
     """
     Run ``n_members`` independent members of ``model`` (additive API, see module docstring).
 
@@ -402,7 +424,7 @@ def integrate_ensemble(model, method='explicit', n_members=None, output='full', 
                        uniforms=uniforms, device=device,
                        count_bits=count_bits, block=block, hist_bins=hist_bins,
                        hist_max=hist_max, hist_times=hist_times, min_blocks=min_blocks,
-                       statistics=statistics, **buffers)
+                       statistics=statistics, moments_from=moments_from, **buffers)
     res.member_offset, res.segment = member_offset, segment
     if check:
         raise_device_error(res.info, method)

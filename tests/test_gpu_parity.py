@@ -432,6 +432,25 @@ def test_streaming_statistics_equal_numpy_over_full_trajectories(method):
             assert list(quant[t, c]) == list(helpers.inverted_cdf_quantiles(counts[t, c], q))
 
 
+@pytest.mark.parametrize('method', ['discrete_time_stochastic', 'continuous_time_stochastic'])
+def test_moments_derived_from_lossless_histograms(method):
+    m = helpers.make_model('strains')
+    m.make_times(0, 50, 1)
+    kw = dict(n_members=2500, output='stats', seed=4, hist_bins=2048, hist_max=2047)
+    ref = m.integrate_ensemble(method, **kw)
+    got = m.integrate_ensemble(method, moments_from='hist', **kw)
+    assert np.array_equal(got.hist, ref.hist) and np.array_equal(got.moments, ref.moments)
+    dev = m.integrate_ensemble(method, moments_from='hist', statistics='device', **kw)
+    assert np.array_equal(dev.moments.cpu().numpy().view(np.uint64), ref.moments)
+    # a count that reaches the last bin cannot be represented: loud error, not wrong moments
+    with pytest.raises(RuntimeError, match='range'):
+        m.integrate_ensemble(method, n_members=500, output='stats', seed=4, hist_bins=512,
+                             hist_max=511, moments_from='hist')
+    with pytest.raises(ValueError, match='width-1'):
+        m.integrate_ensemble(method, n_members=500, output='stats', seed=4, hist_bins=512,
+                             hist_max=4095, moments_from='hist')
+
+
 def test_statistics_large_counts_binned_and_subset_of_times():
     params = dict(helpers.models.SEIR_PARAMS['measles'], population=200000., start_infectious=50.)
     m = helpers.make_model('seird', params=params)

@@ -25,7 +25,11 @@ def main():
     C = cm.n_comp
     kw = dict(output='stats' if out.startswith('stats') else out, seed=1, device=0,
               count_bits=bits, block=block, min_blocks=minb)
-    if out == 'stats':
+    if out == 'stats_histmoments':
+        kw.update(output='stats', hist_bins=2048, hist_max=2047, moments_from='hist',
+                  moments=torch.zeros((T + 1, C, 2), dtype=torch.int64, device=dev),
+                  hist=torch.zeros((T + 1, C, 2048), dtype=torch.int32, device=dev))
+    elif out == 'stats':
         kw.update(hist_bins=2048, hist_max=2047,
                   moments=torch.zeros((T + 1, C, 2), dtype=torch.int64, device=dev),
                   hist=torch.zeros((T + 1, C, 2048), dtype=torch.int32, device=dev))
