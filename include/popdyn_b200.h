@@ -67,6 +67,11 @@ typedef struct {
 #define PD_FLAG_MEMBER_MASK 1   /* the kernel honours pd_*_run.mask (a separate specialisation:
                                    testing for a mask in the general kernel costs 6 % of the
                                    tau-leap step)                                              */
+#define PD_FLAG_HIST_MOMENTS 2  /* PD_STATS kernels without moment accumulators: every run of
+                                   the model sets pd_stoch_run.moments_from_hist and derives the
+                                   moments with pd_hist_moments (a separate specialisation: the
+                                   in-kernel moments are warp-collective, which keeps idle lanes
+                                   and a per-step activity test in the loop)                    */
 
 typedef struct {
   double kernel_ms;       /* device time of the integrator kernel (CUDA events)               */

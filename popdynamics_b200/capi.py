@@ -58,6 +58,7 @@ class ModelDesc(C.Structure):
 
 
 FLAG_MEMBER_MASK = 1
+FLAG_HIST_MOMENTS = 2
 
 
 class RunResult(C.Structure):

@@ -110,9 +110,18 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   const int tid = threadIdx.x;
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + tid;
 #if PD_USE_MASK
-  const bool active = m < a.n_member && a.mask[m < a.n_member ? m : 0] == (unsigned char)a.mask_value;
+  const bool has_member = m < a.n_member && a.mask[m < a.n_member ? m : 0] == (unsigned char)a.mask_value;
 #else
-  const bool active = m < a.n_member;
+  const bool has_member = m < a.n_member;
+#endif
+#if PD_OUT_MODE == PD_OUT_STATS && !PD_HIST_MOMENTS
+  /* the in-kernel moments are warp- and block-collective: lanes without a member stay */
+  const bool active = has_member;
+#else
+  /* nothing below is collective: lanes without a member leave, and the step loop carries no
+   * per-lane activity test */
+  if (!has_member) return;
+  const bool active = true;
 #endif
   const pd_i64 M = a.n_member;
 
@@ -315,9 +324,10 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
     if (!bad && rng.exhausted) bad = PD_ERR_STREAM;
     if (bad) pd_raise(a.err, bad, a.member0 + m, 0);
   }
-  if (a.n_steps) {
-    const pd_u32 lanes = __popc(__ballot_sync(PD_FULL_MASK, active));
-    if ((tid & 31) == 0 && lanes)
-      atomicAdd(a.n_steps, (pd_u64)lanes * (pd_u64)(a.n_time - 1));
+  if (a.n_steps && active) {
+    /* whichever lanes arrive together elect one of them; the groups' counts add up */
+    const pd_u32 group = __activemask();
+    if ((tid & 31) == __ffs(group) - 1)
+      atomicAdd(a.n_steps, (pd_u64)__popc(group) * (pd_u64)(a.n_time - 1));
   }
 }

@@ -207,7 +207,10 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
         # kernel of a large flow table (TB: 20 rows, 84 registers) is better left uncapped
         min_blocks = max(1, 1024 // int(block))
     kernel = _kernel_for(cm, method_code, out_code, rng_code, device, count_bits, block,
-                         min_blocks, capi.FLAG_MEMBER_MASK if mask is not None else 0)
+                         min_blocks,
+                         (capi.FLAG_MEMBER_MASK if mask is not None else 0) |
+                         (capi.FLAG_HIST_MOMENTS if (moments_from == 'hist' and output == 'stats')
+                          else 0))
     C, T, M = cm.n_comp, len(target_times), int(n_members)
     tt = numpy.ascontiguousarray([float(t) for t in target_times], dtype=numpy.float64)
 

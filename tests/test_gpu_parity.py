@@ -451,6 +451,24 @@ def test_moments_derived_from_lossless_histograms(method):
                              hist_max=4095, moments_from='hist')
 
 
+def test_hist_moments_specialisation_must_match_the_run(monkeypatch):
+    """moments_from_hist is a kernel specialisation (PD_FLAG_HIST_MOMENTS): a model built without
+    the flag refuses such a run instead of silently skipping the moments; n_steps and ragged last
+    blocks (members leave the kernel early there) are unaffected."""
+    from popdynamics_b200 import capi
+    m = helpers.make_model('strains')
+    m.make_times(0, 20, 1)
+    kw = dict(n_members=333, output='stats', seed=8, hist_bins=2048, hist_max=2047)
+    ok = m.integrate_ensemble('discrete_time_stochastic', moments_from='hist', **kw)
+    ref = m.integrate_ensemble('discrete_time_stochastic', **kw)
+    assert np.array_equal(ok.moments, ref.moments) and np.array_equal(ok.hist, ref.hist)
+    assert ok.info['n_steps'] == ref.info['n_steps'] == 333 * 20
+    assert int(ok.hist[5].sum()) == 333 * 5
+    monkeypatch.setattr(capi, 'FLAG_HIST_MOMENTS', 0)
+    with pytest.raises(capi.PopdynError, match='PD_FLAG_HIST_MOMENTS'):
+        m.integrate_ensemble('discrete_time_stochastic', moments_from='hist', **kw)
+
+
 def test_statistics_large_counts_binned_and_subset_of_times():
     params = dict(helpers.models.SEIR_PARAMS['measles'], population=200000., start_infectious=50.)
     m = helpers.make_model('seird', params=params)

@@ -1,6 +1,6 @@
 """Compile one model/method/output variant with NVRTC (no GPU needed) and write the cubin, so that
 `cuobjdump -sass` / `nvdisasm` can be run on it.  usage:
-  python tools/dump_sass.py strains discrete_time_stochastic stats 32 256 4 /tmp/k.cubin"""
+  python tools/dump_sass.py strains discrete_time_stochastic stats 32 256 4 /tmp/k.cubin [inject] [--flags N]"""
 import ctypes as C
 import os
 import sys
@@ -24,7 +24,8 @@ def main():
         print(cm.cuda_source())
     k = capi.Model(cm.cuda_source(), capi.METHOD_CODES[method], capi.OUTPUT_CODES[out], rng, 0,
                    cm.n_comp, cm.n_param, len(cm.member_param_slots()), cm.n_su, cm.n_flow,
-                   count_bits=int(bits), block=int(block), min_blocks=int(minb))
+                   count_bits=int(bits), block=int(block), min_blocks=int(minb),
+                   flags=int(sys.argv[sys.argv.index('--flags') + 1]) if '--flags' in sys.argv else 0)
     n = C.c_size_t()
     capi.check(capi.lib().pd_model_cubin_size(k.handle, C.byref(n)))
     buf = C.create_string_buffer(n.value)
