@@ -57,7 +57,9 @@ __device__ __forceinline__ double pd_tau_code(double mean) {
  * the integer count alone while dt is constant.  This kernel evaluates exactly the expression of
  * the rate pass -- rate = (double)n * p; mean = rate * dt; pd_tau_code(mean) -- for n = 0 ..
  * n_entry - 1, so a looked-up code is bit-identical to a computed one.  0.0 marks "the row does
- * not exist / draws nothing" (:712-733, a zero mean), NaN a negative or NaN mean (error). */
+ * not exist / draws nothing" (:712-733, a zero mean), NaN a negative or NaN mean (error): the host
+ * builds a table for a positive dt only, so NaN can only appear among the single codes of the
+ * entry rows. */
 extern "C" __device__ unsigned int pd_tab_count = PD_NTAB;       /* tables of n_entry codes  */
 extern "C" __device__ unsigned int pd_uni_count = PD_NUNI;       /* single codes behind them */
 __device__ const int pd_tab_param[PD_NTAB_DIM] = PD_TAB_PARAMS;
@@ -83,9 +85,8 @@ extern "C" __global__ void pd_tau_table_kernel(const __grid_constant__ PdTauLaun
     const double rate = (double)n * L.U.p[pd_tab_param[t]];
     double code = 0.0;
     if (rate > 0) {
-      const double mean = rate * dt;
+      const double mean = rate * dt;          /* dt > 0: positive, zero (underflow) or +inf */
       if (mean > 0.0) code = pd_tau_code(mean);
-      else if (!(mean == 0.0)) code = __longlong_as_double(0x7ff8000000000000LL);
     }
     table[(size_t)t * n_entry + n] = code;
   }
@@ -184,10 +185,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   if (PD_ROW_TAB_##e >= 0 && use_table && y[from] < (pd_count)a.code_table_n) {      \
     const double code = a.code_table[(PD_ROW_TAB_##e < 0 ? 0 : PD_ROW_TAB_##e) *     \
                                      a.code_table_n + (int)y[from]];                 \
-    if (code != 0.0) {                                                               \
-      if (code != code) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
-      else PD_TAU_APPEND(e, code)                                                    \
-    }                                                                                \
+    if (code != 0.0) PD_TAU_APPEND(e, code)       /* never NaN: the table's dt is > 0 */ \
   } else PD_TAU_COMPUTED(e, rate)
 #define PD_TAU_ENTRY(e, to, is_int, rate)                                            \
   if (PD_ROW_UNI_##e >= 0 && use_table) {                                            \
