@@ -63,26 +63,37 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   bool any = false;            /* a live event has been seen                     */
   bool on_float_path = false;  /* sum() has met its first float                  */
   int last = -1;
-#define PD_ACC(e, is_int)                                                            \
+/* One row joins the running sums.  Branch-free: a dead row (rate not > 0, :712-733) adds +0.0,
+ * which changes neither the cumulative sum nor the compensated one (t == f, the correction term
+ * is (f - f) + 0), so every lane executes the same straight-line code and nothing has to be
+ * merged after a branch.  Python's sum() adds its first float with a plain `+` and compensates
+ * from the second one on (on_float_path). */
+#define PD_ACC_INT(e)                                                                \
+  { cum += r[e]; cumul[e] = cum; last = e; any = true; if (!PD_NAIVE_SUM) f += r[e]; }
+#define PD_ACC_FLOAT(e, live_)                                                       \
   {                                                                                  \
-    cum += r[e]; cumul[e] = cum; last = e; any = true;                               \
-    if (PD_NAIVE_SUM) { /* total == cum */ }                                         \
-    else if (is_int) f += r[e];                                                      \
-    else if (!on_float_path) { f = f + r[e]; on_float_path = true; }                 \
-    else {                                                                           \
-      const double t = f + r[e];                                                     \
-      if (fabs(f) >= fabs(r[e])) comp += (f - t) + r[e]; else comp += (r[e] - t) + f;\
-      f = t;                                                                         \
+    const bool lv = (live_);                                                         \
+    const double rr = lv ? r[e] : 0.0;                                               \
+    cum += rr; cumul[e] = lv ? cum : -1.0; last = lv ? e : last; any |= lv;          \
+    if (!PD_NAIVE_SUM) {                                                             \
+      const double t = f + rr;                                                       \
+      const bool big = fabs(f) >= fabs(rr);                                          \
+      const double hi = big ? f : rr, lo = big ? rr : f;                             \
+      const double ci = (hi - t) + lo;                                               \
+      comp += on_float_path ? ci : 0.0;                                              \
+      f = t; on_float_path |= lv;                                                    \
     }                                                                                \
   }
-#define PD_G1_ENTRY(e, to, is_int, rate) r[e] = rate; PD_ACC(e, is_int)
-#define PD_G1_TRANSFER(e, from, to, rate) r[e] = rate; if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
-#define PD_G1_DEATH(e, from, rate) r[e] = rate; if (r[e] > 0) PD_ACC(e, 0) else cumul[e] = -1.0;
+#define PD_G1_ENTRY(e, to, is_int, rate)                                             \
+  r[e] = rate; if (is_int) PD_ACC_INT(e) else PD_ACC_FLOAT(e, true)
+#define PD_G1_TRANSFER(e, from, to, rate) r[e] = rate; PD_ACC_FLOAT(e, r[e] > 0)
+#define PD_G1_DEATH(e, from, rate) r[e] = rate; PD_ACC_FLOAT(e, r[e] > 0)
   PD_FOR_EACH_LIVE_ROW(PD_G1_ENTRY, PD_G1_TRANSFER, PD_G1_DEATH)
 #undef PD_G1_ENTRY
 #undef PD_G1_TRANSFER
 #undef PD_G1_DEATH
-#undef PD_ACC
+#undef PD_ACC_INT
+#undef PD_ACC_FLOAT
 
   if (!any) {                                   /* :767-770 */
     const double dt = new_time - time;
