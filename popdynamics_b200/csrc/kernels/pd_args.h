@@ -68,25 +68,18 @@ typedef struct {
   int pad2;
 } PdStochArgs;
 
-/* Streaming statistics are reduced once per EPOCH of PD_EPOCH recorded target times: a lane keeps
- * walking its own trajectory and parks the counts of each recorded time in a shared-memory ring;
- * at the end of the epoch the block reduces the ring row by row (pd_common.cuh).               */
+/* The tau-leap kernel keeps per-warp partial moment sums in shared memory and moves them to
+ * global memory once per EPOCH of PD_EPOCH recorded target times (pd_common.cuh).              */
 #ifndef PD_EPOCH
-#define PD_EPOCH 16      /* warp-synchronous recording (tau-leap): per-warp partial sums      */
-#endif
-#ifndef PD_RING_EPOCH
-#define PD_RING_EPOCH 4  /* lane-asynchronous recording (Gillespie): ring of parked counts    */
+#define PD_EPOCH 16
 #endif
 
 /* Dynamic shared memory of the stochastic kernels (each kernel exports its total as the device
  * symbol pd_smem_bytes, which the host reads after loading the module):
  *   tau-leap : the draw list     double   [n_row][block]   (n_row = flow-table rows that can fire)
- *   Gillespie, PD_OUT_STATS: counts ring  count_t [PD_RING_EPOCH][n_comp][block]              */
+ *   Gillespie, FULL / STATS output: the recording window  count_t [slots][n_comp][block]       */
 #define PD_ALIGN8(x) (((x) + 7) & ~(size_t)7)
 #define PD_CODE_SMEM_BYTES(n_row, block) ((size_t)((n_row) > 0 ? (n_row) : 1) * (size_t)(block) * 8)
-#define PD_RING_SMEM_BYTES(n_slot, n_comp, block, count_bytes)                             \
-  PD_ALIGN8((size_t)(n_slot) * (size_t)(n_comp) * (size_t)(block) * (size_t)(count_bytes))
-
 typedef struct {
   long long n_member;
   const double *y0;

@@ -15,10 +15,15 @@
  * `sum(rates)` is Python's builtin: Neumaier-compensated on CPython >= 3.12 (PD_NAIVE_SUM 0) or
  * the plain left fold (PD_NAIVE_SUM 1), in which case it equals the last cumulative sum.
  *
- * Divergence: every lane walks its own target index (flattened loop), so in FULL / FINAL mode a
- * warp only idles at the very end of its longest member; STATS mode parks the counts in a
- * shared-memory ring and synchronises the block once per epoch of PD_RING_EPOCH target times, where
- * the ring is reduced row by row (pd_common.cuh).
+ * Divergence: every lane walks its own target index (flattened loop), so a warp only idles at the
+ * very end of its longest member.  Recording (FULL / STATS output) must not happen inside that
+ * divergent walk -- a handful of lanes cross a target time in any given trip, and the record code
+ * run for them alone cost 75 % of the kernel.  Instead a lane PARKS its counts in its own column
+ * of a shared-memory window of PD_GIL_SLOTS target times (five cheap stores) and keeps going; once
+ * per trip one REDUX.MIN finds the oldest target time every lane of the WARP has passed, and the
+ * warp records those slots together, all 32 lanes on: coalesced rows of the trajectory, one RED
+ * per count into the histograms, one REDUX per moment.  A lane that gets PD_GIL_SLOTS target times
+ * ahead of the slowest lane of its warp waits for it; there is no block-level barrier.
  */
 #include "pd_model.h"
 #include "pd_common.cuh"
@@ -28,11 +33,16 @@ struct PdGilLaunch {
   PdUniform U;
 };
 
-/* the kernel's dynamic shared memory, read by the host after loading the module
- * (csrc/popdyn_capi.cu) */
+/* the kernel's dynamic shared memory (the recording window), read by the host after loading the
+ * module (csrc/popdyn_capi.cu) */
+#define PD_GIL_WINDOW (PD_OUT_MODE != PD_OUT_FINAL)
+/* window slots: the largest power of two in [2, 16] that keeps the window near 40 KB per block */
+#define PD_GIL_SLOT_BYTES ((int)(PD_C * PD_BLOCK * sizeof(pd_count)))
+#define PD_GIL_SLOTS                                                                   \
+  (16 * PD_GIL_SLOT_BYTES <= 40960 ? 16 : 8 * PD_GIL_SLOT_BYTES <= 40960 ? 8           \
+   : 4 * PD_GIL_SLOT_BYTES <= 40960 ? 4 : 2)
 extern "C" __device__ unsigned int pd_smem_bytes =
-    (PD_OUT_MODE == PD_OUT_STATS)
-        ? (unsigned int)PD_RING_SMEM_BYTES(PD_RING_EPOCH, PD_C, PD_BLOCK, sizeof(pd_count)) : 0u;
+    PD_GIL_WINDOW ? (unsigned int)(PD_GIL_SLOTS * PD_GIL_SLOT_BYTES) : 0u;
 
 /* the two uniforms of one reaction: exactly one Philox block when no spare is pending */
 __device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdPhilox &rng, double &u1,
@@ -151,12 +161,9 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
 #endif
   const pd_i64 M = a.n_member;
 
-#if PD_OUT_MODE == PD_OUT_STATS
+#if PD_GIL_WINDOW
   extern __shared__ double s_dyn[];
-  pd_count *s_ring = (pd_count *)s_dyn;                     /* [PD_RING_EPOCH][PD_C][PD_BLOCK] */
-  const pd_i64 block_member0 = (pd_i64)blockIdx.x * PD_BLOCK;
-  const int n_active = (M - block_member0 < PD_BLOCK) ? (int)(M - block_member0) : PD_BLOCK;
-  __syncthreads();
+  pd_count *const s_col = (pd_count *)s_dyn + threadIdx.x;  /* [slot][c][PD_BLOCK], own column */
 #endif
 
   pd_count y[PD_C];
@@ -184,43 +191,53 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
   pd_u64 n_event = 0;
   double time = a.target[0];
 
-#if PD_OUT_MODE == PD_OUT_STATS
-  /* Epochs of PD_RING_EPOCH target times.  Inside an epoch the (target, event) loops are flattened as
-   * in the other modes: a lane parks its counts in the ring when it crosses a target time and
-   * keeps going, so a warp only waits for its slowest lane once per epoch; then the block
-   * reduces the ring (pd_stats_flush, two barriers inside). */
-  for (int it0 = 0; it0 < a.n_time; it0 += PD_RING_EPOCH) {
-    const int it1 = (it0 + PD_RING_EPOCH < a.n_time) ? it0 + PD_RING_EPOCH : a.n_time;
-    if (active) {
-      int it = it0;
-      for (;;) {
-        while (it < it1 && (it == 0 || bad || !(time < a.target[it]))) {
+#if PD_GIL_WINDOW
+  /* FULL: row 0 is the untruncated y written above; STATS: target 0 goes through the window */
+  const int first = (PD_OUT_MODE == PD_OUT_FULL) ? 1 : 0;
+  int it = active ? first : a.n_time;          /* next target time this lane has to park     */
+  int flushed = first;                         /* warp-uniform: targets below it are recorded */
+  for (;;) {
+    /* park every target time already reached (:762 false -> :793-795), window permitting; a
+     * failed member parks its last counts for the rest so that the warp can finish */
+    while (it < a.n_time && it - flushed < PD_GIL_SLOTS &&
+           (it == 0 || bad || !(time < a.target[it]))) {
 #pragma unroll
-          for (int c = 0; c < PD_C; ++c)
-            s_ring[((it - it0) * PD_C + c) * PD_BLOCK + threadIdx.x] = y[c];   /* :793-795 */
-          ++it;
-        }
-        if (it >= it1) break;
-        bad = pd_gillespie_event(a, L.U, pm, y, time, a.target[it], rng, n_event);   /* :762 */
-      }
+      for (int c = 0; c < PD_C; ++c)
+        s_col[((it & (PD_GIL_SLOTS - 1)) * PD_C + c) * PD_BLOCK] = y[c];
+      ++it;
     }
-    pd_stats_flush(a, s_ring, it0, it1 - it0, n_active, a.member0 + block_member0);
+    /* record, all lanes together, what every lane of the warp has parked */
+    const int ready = __reduce_min_sync(PD_FULL_MASK, it);
+    while (flushed < ready) {
+      pd_count ys[PD_C];
+#pragma unroll
+      for (int c = 0; c < PD_C; ++c)
+        ys[c] = s_col[((flushed & (PD_GIL_SLOTS - 1)) * PD_C + c) * PD_BLOCK];
+#if PD_OUT_MODE == PD_OUT_FULL
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < PD_C; ++c)
+          a.soln[((size_t)flushed * PD_C + c) * M + m] = (double)ys[c];
+      }
+#elif PD_HIST_MOMENTS
+      if (active) pd_hist_record(a, ys, flushed, a.member0 + m);
+#else
+      pd_stats_warp_record(a, ys, active, flushed, a.member0 + m);
+#endif
+      ++flushed;
+    }
+    if (flushed >= a.n_time) break;
+    /* one reaction for every lane that is still inside its current interval (:762) */
+    if (it < a.n_time && !bad && time < a.target[it])
+      bad = pd_gillespie_event(a, L.U, pm, y, time, a.target[it], rng, n_event);
   }
 #else
   if (active) {
     /* Every trip of the loop is one reaction for EVERY unfinished lane: a lane first steps over
-     * the target times it has already reached (a short predicated loop, usually no trip), so
-     * that recording never takes a warp-wide turn of its own. */
+     * the target times it has already reached (a short predicated loop, usually no trip). */
     int it = 1;
     for (;;) {
-      while (it < a.n_time && !(time < a.target[it])) {      /* :762 false -> record, :793-795 */
-#if PD_OUT_MODE == PD_OUT_FULL
-#pragma unroll
-        for (int c = 0; c < PD_C; ++c)
-          a.soln[((size_t)it * PD_C + c) * M + m] = (double)y[c];
-#endif
-        ++it;
-      }
+      while (it < a.n_time && !(time < a.target[it])) ++it;  /* :762 false */
       if (it >= a.n_time) break;
       bad = pd_gillespie_event(a, L.U, pm, y, time, a.target[it], rng, n_event);
       if (bad) break;

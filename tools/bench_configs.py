@@ -46,6 +46,8 @@ CONFIGS = {
                     (0, 1000, 1), 1 << 20, 'final', 2000),
     'strains_cts_stats': (lambda n, rng: models.StrainsModel(), 'continuous_time_stochastic',
                           (0, 1000, 1), 1 << 20, 'stats', 2000),
+    'strains_cts_stats_hist': (lambda n, rng: models.StrainsModel(), 'continuous_time_stochastic',
+                               (0, 1000, 1), 1 << 20, 'stats_hist', 2000),
     'strains_dts_full': (lambda n, rng: models.StrainsModel(), 'discrete_time_stochastic',
                          (0, 200, 1), 1 << 20, 'full', 2000),
     # BASELINE config 4: TB model with its scale-ups evaluated inside the stochastic loops
@@ -68,7 +70,11 @@ def run(name, reps=3):
     y = model.get_init_list()
     C, T = cm.n_comp, len(model.target_times)
     dev = torch.device('cuda:0')
+    moments_from = 'hist' if output == 'stats_hist' else 'kernel'
+    output = output.split('_')[0]
     kw = dict(output=output, seed=1, device=0)
+    if output == 'stats':
+        kw['moments_from'] = moments_from
     if method != 'explicit':
         kw.update(count_bits=32, block=256)
     if output == 'final':
@@ -89,7 +95,8 @@ def run(name, reps=3):
         best = min(best, res.info['kernel_ms'])
     steps = int(res.info['n_steps'])        # member-steps (explicit, DTS) or events (CTS)
     line = {'config': name, 'method': method, 'members': M, 'n_time': T, 'compartments': C,
-            'output': output, 'steps': steps, 'kernel_ms': best,
+            'output': output + ('/moments from hist' if moments_from == 'hist' else ''),
+            'steps': steps, 'kernel_ms': best,
             'steps_per_s': steps / (best * 1e-3), 'comp_steps_per_s': steps * C / (best * 1e-3),
             'regs': res.info['regs_per_thread'], 'blocks_per_sm': res.info['blocks_per_sm'],
             'block': res.info['block']}
