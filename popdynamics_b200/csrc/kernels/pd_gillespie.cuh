@@ -38,9 +38,11 @@ struct PdGilLaunch {
 #define PD_GIL_WINDOW (PD_OUT_MODE != PD_OUT_FINAL)
 /* window slots: the largest power of two in [2, 16] that keeps the window near 40 KB per block */
 #define PD_GIL_SLOT_BYTES ((int)(PD_C * PD_BLOCK * sizeof(pd_count)))
+#ifndef PD_GIL_SLOTS
 #define PD_GIL_SLOTS                                                                   \
   (16 * PD_GIL_SLOT_BYTES <= 40960 ? 16 : 8 * PD_GIL_SLOT_BYTES <= 40960 ? 8           \
    : 4 * PD_GIL_SLOT_BYTES <= 40960 ? 4 : 2)
+#endif
 extern "C" __device__ unsigned int pd_smem_bytes =
     PD_GIL_WINDOW ? (unsigned int)(PD_GIL_SLOTS * PD_GIL_SLOT_BYTES) : 0u;
 
