@@ -58,6 +58,8 @@ __device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdInject &
   u2 = rng.next(a);
 }
 
+#define PD_GIL_WORDS ((PD_NFLOW_DIM + 31) / 32)   /* words of a flow-table row mask */
+
 /* one reaction: returns the error code (0 = ok); advances time, mutates y */
 __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const PdUniform &U,
                                                   const double (&pm)[PD_NPM_DIM],
@@ -69,24 +71,28 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   for (int c = 0; c < PD_C; ++c) yd[c] = (double)y[c];
   pd_event_mults(yd, U, pm, time, (const double *)0, mult);
 
-  /* pass 1: cumulative intervals over the live events + Python's sum() */
+  /* pass 1: cumulative intervals over the live events + Python's sum().  Which rows are live is
+   * kept as a bit mask (row indices are literals, so word and bit resolve at compile time). */
   double cum = 0.0;            /* cumul_interval, :170-173                      */
   double f = 0.0, comp = 0.0;  /* sum(): running value and Neumaier compensation */
-  bool any = false;            /* a live event has been seen                     */
   bool on_float_path = false;  /* sum() has met its first float                  */
-  int last = -1;
+  pd_u32 live[PD_GIL_WORDS];
+#pragma unroll
+  for (int w = 0; w < PD_GIL_WORDS; ++w) live[w] = 0;
+#define PD_SETBIT(words, e, p) words[(e) >> 5] |= (pd_u32)(p) << ((e) & 31)
 /* One row joins the running sums.  Branch-free: a dead row (rate not > 0, :712-733) adds +0.0,
  * which changes neither the cumulative sum nor the compensated one (t == f, the correction term
  * is (f - f) + 0), so every lane executes the same straight-line code and nothing has to be
- * merged after a branch.  Python's sum() adds its first float with a plain `+` and compensates
- * from the second one on (on_float_path). */
+ * merged after a branch; its cumul[] entry repeats the previous one and is never looked at
+ * (pass 2 masks with the live bits).  Python's sum() adds its first float with a plain `+` and
+ * compensates from the second one on (on_float_path). */
 #define PD_ACC_INT(e)                                                                \
-  { cum += r[e]; cumul[e] = cum; last = e; any = true; if (!PD_NAIVE_SUM) f += r[e]; }
+  { cum += r[e]; cumul[e] = cum; PD_SETBIT(live, e, 1); if (!PD_NAIVE_SUM) f += r[e]; }
 #define PD_ACC_FLOAT(e, live_)                                                       \
   {                                                                                  \
     const bool lv = (live_);                                                         \
     const double rr = lv ? r[e] : 0.0;                                               \
-    cum += rr; cumul[e] = lv ? cum : -1.0; last = lv ? e : last; any |= lv;          \
+    cum += rr; cumul[e] = cum; PD_SETBIT(live, e, lv);                               \
     if (!PD_NAIVE_SUM) {                                                             \
       const double t = f + rr;                                                       \
       const bool big = fabs(f) >= fabs(rr);                                          \
@@ -107,6 +113,9 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
 #undef PD_ACC_INT
 #undef PD_ACC_FLOAT
 
+  pd_u32 any = 0;
+#pragma unroll
+  for (int w = 0; w < PD_GIL_WORDS; ++w) any |= live[w];
   if (!any) {                                   /* :767-770 */
     const double dt = new_time - time;
     time += dt;
@@ -127,17 +136,28 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   const double dt = -log(u2) / total;
 
   /* pass 2: first live event with not (point > cumul), else the last live one (:176-177) */
-  int sel = -1;
-#define PD_PICK(e) if (sel < 0 && cumul[e] >= 0.0 && !(point > cumul[e])) sel = e;
-#define PD_G2_ENTRY(e, to, is_int, rate) if (sel < 0 && !(point > cumul[e])) sel = e;
-#define PD_G2_TRANSFER(e, from, to, rate) PD_PICK(e)
-#define PD_G2_DEATH(e, from, rate) PD_PICK(e)
+  pd_u32 above[PD_GIL_WORDS];                   /* rows with point > cumul[e] */
+#pragma unroll
+  for (int w = 0; w < PD_GIL_WORDS; ++w) above[w] = 0;
+#define PD_G2_ENTRY(e, to, is_int, rate) PD_SETBIT(above, e, point > cumul[e]);
+#define PD_G2_TRANSFER(e, from, to, rate) PD_SETBIT(above, e, point > cumul[e]);
+#define PD_G2_DEATH(e, from, rate) PD_SETBIT(above, e, point > cumul[e]);
   PD_FOR_EACH_LIVE_ROW(PD_G2_ENTRY, PD_G2_TRANSFER, PD_G2_DEATH)
 #undef PD_G2_ENTRY
 #undef PD_G2_TRANSFER
 #undef PD_G2_DEATH
-#undef PD_PICK
-  if (sel < 0) sel = last;
+#undef PD_SETBIT
+  int sel = -1;
+#pragma unroll
+  for (int w = 0; w < PD_GIL_WORDS; ++w) {
+    const pd_u32 hit = live[w] & ~above[w];
+    if (sel < 0 && hit) sel = w * 32 + __ffs(hit) - 1;
+  }
+  if (sel < 0) {
+#pragma unroll
+    for (int w = PD_GIL_WORDS - 1; w >= 0; --w)
+      if (sel < 0 && live[w]) sel = w * 32 + 31 - __clz(live[w]);
+  }
 
   /* apply +-1 (:778-787) */
 #define PD_G3_ENTRY(e, to, is_int, rate) if (sel == e) y[to] += 1;
