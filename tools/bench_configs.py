@@ -76,7 +76,9 @@ def run(name, reps=3):
     if output == 'stats':
         kw['moments_from'] = moments_from
     if method != 'explicit':
-        kw.update(count_bits=32, block=256)
+        kw.update(count_bits=32, block=int(os.environ.get('PD_BENCH_BLOCK', 256)))
+        if os.environ.get('PD_BENCH_MIN_BLOCKS'):
+            kw['min_blocks'] = int(os.environ['PD_BENCH_MIN_BLOCKS'])
     if output == 'final':
         kw['out'] = torch.zeros((C, M), dtype=torch.float64, device=dev)
     elif output == 'full':
