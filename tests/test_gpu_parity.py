@@ -220,6 +220,47 @@ def test_injected_stream_golden_runs_of_the_reference(golden):
             assert np.array_equal(res.soln[:, :, k], golden['strains_%s_inject%d' % (tag, k)])
 
 
+@pytest.mark.parametrize('output', ['full', 'stats', 'final'])
+def test_gillespie_failed_member_does_not_stall_its_warp(output):
+    """One member hits log(0) (u2 == 0, basepop.py:776 raises there) in the middle of its run.  The
+    recording window must let its warp finish, the error must name the member, and with full
+    output every other member still equals the oracle."""
+    from popdynamics_b200 import ensemble
+    method = 'continuous_time_stochastic'
+    m = helpers.make_model('strains')
+    m.make_times(0, 30, 1)
+    n = 70
+    u = np.random.default_rng(21).random((4000, n))
+    u[41, 3] = 0.0                                  # the second uniform of member 3's 21st event
+    cm = helpers.compiled(m, method)
+    kw = dict(output=output, uniforms=u)
+    if output == 'stats':
+        kw.update(hist_bins=2048, hist_max=2047)
+    res = ensemble.run_compiled(m, cm, method, m.get_init_list(), m.target_times, n, **kw)
+    assert res.info['err_code'] == 5 and res.info['err_member'] == 3
+    with pytest.raises(ValueError, match='math domain error'):
+        ensemble.raise_device_error(res.info, method)
+    if output == 'full':
+        om = oracle.OracleModel(cm)
+        for i in (0, 2, 4, 31, 32, 69):
+            want, _, err = om.gillespie(m.get_init_list(), m.target_times,
+                                        oracle.Rng('inject', uniforms=u[:, i].copy()))
+            assert err == 0 and np.array_equal(res.soln[:, :, i], want)
+
+
+@pytest.mark.parametrize('method', ['discrete_time_stochastic', 'continuous_time_stochastic'])
+def test_single_target_time_records_the_initial_state(method):
+    m = helpers.make_model('strains')
+    m.target_times = [0.]
+    y0 = np.array(m.get_init_list(), dtype=np.int64)
+    stats = m.integrate_ensemble(method, n_members=45, output='stats', seed=1, hist_bins=2048,
+                                 hist_max=2047)
+    assert np.array_equal(stats.moments[0, :, 0].astype(np.int64), 45 * y0)
+    assert [int(stats.hist[0, c, y0[c]]) for c in range(5)] == [45] * 5
+    full = m.integrate_ensemble(method, n_members=45, output='full', seed=1)
+    assert full.soln.shape == (1, 5, 45) and np.array_equal(full.soln[0, :, 7], y0)
+
+
 def test_exhausted_stream_is_reported():
     m = helpers.make_model('strains')
     m.make_times(0, 50, 1)
