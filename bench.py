@@ -42,12 +42,12 @@ HIST_MAX = 2047          # strains counts stay well below 2048 (S ~ 1000-2000): 
 #   implementation (which needs fewer: see USEFUL_INST).
 #   USEFUL_INST_PER_MEMBER_STEP: predicated-on thread instructions the current kernel executes
 #   per member-step (ncu thread_inst_executed_true / member-steps of the captured launch,
-#   profiles/r1_tau_leap_stats_bench_ncu_summary.txt): 1.971e12 / 2e9.
+#   profiles/r1_tau_leap_stats_bench_ncu_summary.txt): 1.914e12 / 2e9.
 #   DRAM_BYTES_PER_MEMBER_STEP: dram__bytes_read + write of the same capture per member-step
 #   (8.28 MB over 2e9 member-steps); the streaming-statistics mode reads y0 once and writes
 #   nothing per step.
 ALGORITHMIC_OPS_PER_MEMBER_STEP = 1300.0
-USEFUL_INST_PER_MEMBER_STEP = 985.0
+USEFUL_INST_PER_MEMBER_STEP = 957.0
 DRAM_BYTES_PER_MEMBER_STEP = 0.0041
 SM_COUNT = 148
 LANES_PER_SM_PER_CLK = 128          # 4 schedulers x 1 warp instruction x 32 lanes
