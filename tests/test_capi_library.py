@@ -30,6 +30,18 @@ def test_header_symbols_are_all_exported(built_library):
     assert sorted(capi.EXPORTED_SYMBOLS) == names
 
 
+def test_header_constants_match_the_binding():
+    text = open(os.path.join(ROOT, 'include', 'popdyn_b200.h')).read()
+    defines = dict(re.findall(r'#define\s+(PD_[A-Z_0-9]+)\s+(-?\d+)\b', text))
+    assert int(defines['PD_FLAG_MEMBER_MASK']) == capi.FLAG_MEMBER_MASK
+    assert int(defines['PD_FLAG_HIST_MOMENTS']) == capi.FLAG_HIST_MOMENTS
+    enums = dict(re.findall(r'\b(PD_[A-Z_]+)\s*=\s*(-?\d+)', text))
+    assert int(enums['PD_DIAGNOSTICS']) == capi.DIAGNOSTICS
+    for name, value in capi.METHOD_CODES.items():
+        assert value in (0, 1, 2)
+    assert int(enums['PD_E_INVALID']) < 0 and int(enums['PD_E_NO_DEVICE']) == capi.PD_E_NO_DEVICE
+
+
 def test_version_and_device_count(built_library):
     assert capi.lib().pd_version() == 100
     assert capi.device_count() >= 0
