@@ -197,7 +197,10 @@ int pd_philox_fill(double *out, int64_t n, int64_t n_member, int64_t member0, ui
                    int32_t device, void *stream);
 /* Pipe-peak microbenchmarks for the roofline denominators MEASURED_PEAKS.json lacks:
  * kind 0 = fp64 DADD+DMUL (non-fused, what --fmad=false code issues), 1 = fp64 DFMA,
- * 2 = int32 IMAD/LOP3 mix as in Philox.  Returns giga-operations per second.                  */
+ * 2 = int32 IMAD/LOP3 mix as in Philox (3 operations per element, issued as IMAD.WIDE.U32 + LOP3).
+ * Kinds 3, 4, 5 count ELEMENTS per second of a dependent chain of IMAD.HI.U32 + LOP3, IMAD (low
+ * half) + LOP3, and SHF + LOP3: they show what one Philox multiply costs on the FMA-heavy pipe.
+ * Returns giga-operations (giga-elements) per second.                                          */
 int pd_microbench(int32_t kind, int32_t device, double *gops);
 
 #ifdef __cplusplus
