@@ -3,15 +3,25 @@
 """
 Headline benchmark: trajectory-compartment-steps/sec of the multi-strain SIR ensemble
 (BASELINE.json config 3: examples/stochastic_strains_model.py, discrete-time stochastic,
-10^7 members per GPU, make_times(0, 1000, 1), ensemble mean / variance / quantiles).
+10^7 members per GPU, make_times(0, 1000, 1), ensemble mean / variance / quantiles), plus the
+other BASELINE.json configurations at their stated sizes as a ``configs`` list in the same line.
 
     python bench.py --gpus N --steps K --warmup W            # this framework, N GPUs (torchrun for N>1)
-    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on host cores
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the reference's loop on host cores
 
 One "step" = one pass of the hot path over the whole ensemble: M members x 1000 tau-leap steps,
-statistics fused, plus (N > 1) the NCCL all-reduce of the integer moments / histograms and the
-quantile kernel.  ``value`` is measured with the statistics buffers resident in HBM, ``e2e``
+statistics fused, plus (N > 1) the NCCL all-reduce of the integer histograms and the moment /
+quantile kernels.  ``value`` is measured with the statistics buffers resident in HBM, ``e2e``
 through the public Python API (``BaseModel.integrate_ensemble``) with host numpy buffers.
+
+``configs`` (outside the headline's timed region, one entry each with its own ms / value / e2e /
+roofline / cpu_baseline / parity spot-check; ``--configs headline`` skips them):
+  2  SEIR with demography, 10^6-member parameter sweep x 50 years, explicit fp64
+  4  TB model, Gillespie, 1950 -> 2000, 125 000 members per GPU (10^6 on 8 GPUs)
+  5  RMIT TB calibration sweep, 10^8 members over the N ranks, output = proportion per member
+  5b mix_model hybrid stochastic / deterministic switching, 2^20 members per GPU
+  6  adaptive (odeint-equivalent) solver on the SEIR-demography sweep
+``strong_scaling``: the headline with 10^7 members in total over the N ranks.
 Prints ONE JSON line on rank 0.
 """
 
@@ -34,23 +44,17 @@ T_END = 1000
 QUANTILES = [0.025, 0.25, 0.5, 0.75, 0.975]
 HIST_BINS = 2048
 HIST_MAX = 2047          # strains counts stay well below 2048 (S ~ 1000-2000): width-1 bins
-# Roofline unit costs of pd_tau_leap_kernel on this workload.  The kernel
-# is bound by SM instruction issue, so the work unit is the thread-operation.
-#   ALGORITHMIC_OPS_PER_MEMBER_STEP: SURVEY.md 8(d)'s per-unit figure for the strains model --
-#   S Poisson draws x (one exp ~ 25-30 fp64 ops + (lambda + 1) uniforms x ~45 int32 Philox ops)
-#   ~ 300 fp64 + ~1000 int32 operations per member-step.  It does not depend on this
-#   implementation (which needs fewer: see USEFUL_INST).
-#   USEFUL_INST_PER_MEMBER_STEP: predicated-on thread instructions the current kernel executes
-#   per member-step (ncu thread_inst_executed_true / member-steps of the captured launch,
-#   profiles/r1_tau_leap_stats_bench_ncu_summary.txt): 1.914e12 / 2e9.
-#   DRAM_BYTES_PER_MEMBER_STEP: dram__bytes_read + write of the same capture per member-step
-#   (8.28 MB over 2e9 member-steps); the streaming-statistics mode reads y0 once and writes
-#   nothing per step.
-ALGORITHMIC_OPS_PER_MEMBER_STEP = 1300.0
-USEFUL_INST_PER_MEMBER_STEP = 957.0
-DRAM_BYTES_PER_MEMBER_STEP = 0.0041
 SM_COUNT = 148
 LANES_PER_SM_PER_CLK = 128          # 4 schedulers x 1 warp instruction x 32 lanes
+# SURVEY.md 8(d)'s back-of-envelope unit for the strains tau-leap step (S Poisson draws x (one exp
+# ~ 25-30 fp64 ops + (lambda + 1) uniforms x ~45 int32 Philox ops) ~ 300 fp64 + ~1000 int32): kept
+# as a NAMED SIDE VALUE (`frac_survey_unit`).  `roofline.frac` itself is counter based: useful
+# (predicated-on) thread-instructions the kernel executes per member-step, from the committed ncu
+# capture below, over the SM issue peak.
+SURVEY_OPS_PER_MEMBER_STEP = 1300.0
+NCU_UNIT_FILE = os.path.join(ROOT, 'profiles', 'r2_tau_leap_headline_ncu.json')
+# fp64 operations per derivative evaluation, SURVEY.md 8(d): V + E + 3(Fv+Ff+D) + 3C + 2C + ~3
+EXPLICIT_OPS = {'seir': 39.0, 'rmit': 84.0}
 
 
 def workload_name(members_per_gpu):
@@ -60,10 +64,13 @@ def workload_name(members_per_gpu):
 
 
 def make_model():
-    from examples import models
-    model = models.StrainsModel()
-    model.make_times(0, T_END, 1)
-    return model
+    from examples import configs
+    return configs.strains()
+
+
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') \
+        else (os.cpu_count() or 1)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -131,14 +138,24 @@ def measured_peaks():
     return {'hbm_gbs': 6650.0}, 'fallback'
 
 
+def ncu_unit():
+    """Per-member-step unit costs of pd_tau_leap_kernel from the committed ncu capture
+    (written by tools/ncu_summary.py --json): useful thread-instructions and DRAM bytes."""
+    if not os.path.exists(NCU_UNIT_FILE):
+        return None
+    with open(NCU_UNIT_FILE) as handle:
+        return json.load(handle)
+
+
 # ---------------------------------------------------------------------------------------------
-def cpu_arm(n_member, n_thread=0):
-    """The reference's algorithm on host cores: oracle port (C, OpenMP), same workload.  All host
-    cores are used whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+# CPU arms.  The oracle (oracle/) is test infrastructure: it is executed here ONLY as the CPU
+# baseline, never on the measured GPU path.
+# ---------------------------------------------------------------------------------------------
+def port_arm(n_member, n_thread=0):
+    """The reference's algorithm on host cores: oracle port (C, OpenMP), the headline workload.
+    All host cores are used whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
     from oracle import oracle
-    if not n_thread:
-        n_thread = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') \
-            else (os.cpu_count() or 1)
+    n_thread = n_thread or host_threads()
     from popdynamics_b200 import compiler
     model = make_model()
     model.check_flow_transfers()
@@ -152,42 +169,91 @@ def cpu_arm(n_member, n_thread=0):
     return out['n_steps'] * len(model.labels) / dt, dt, n_thread
 
 
-def sized_cpu_sample(target_seconds):
-    rate, dt, cores = cpu_arm(2000)
+def sized_port_sample(target_seconds):
+    rate, dt, cores = port_arm(2000)
     n_member = max(2000, int(target_seconds * rate / (T_END * 5)))
     return n_member, cores
 
 
+def port_baseline(seconds):
+    members, cores = sized_port_sample(seconds)
+    value, dt, cores = port_arm(members)
+    return {'value': value, 'unit': 'comp-steps/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d members x 1000 steps x 5 compartments (%.1f s), OpenMP over members; C '
+                      'restatement of basepop.py:797-852 (oracle/popdyn_oracle.c)'
+                      % (members, dt)}
+
+
+def reference_python_baseline(seconds):
+    """The UNMODIFIED reference's own Python loop (oracle/_ref, compiled here from
+    /root/reference by `make -C oracle _ref`) on every host core; None when it did not ship."""
+    try:
+        from oracle import ref_runner
+    except ImportError:
+        return None
+    if not ref_runner.available():
+        return None
+    return ref_runner.time_strains_dts(seconds, host_threads())
+
+
 def run_reference_arm(args):
+    """CPU arm: the reference's own implementation of the headline path on every host core --
+    the unmodified Python loop from oracle/_ref when it shipped with this run, else the oracle
+    port.  Each step is a bounded sample of the workload."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_member, cores = sized_cpu_sample(2.0)
-    for _ in range(args.warmup):
-        cpu_arm(max(500, n_member // 4))
-    t0 = time.perf_counter()
-    total = 0.0
-    for _ in range(args.steps):
-        rate, dt, cores = cpu_arm(n_member)
-        total += n_member * T_END * 5
-    elapsed = time.perf_counter() - t0
-    value = total / elapsed
-    sample = ('%d members x %d tau-leap steps x 5 compartments per step, streaming moments, '
-              'OpenMP over members' % (n_member, T_END))
+    cores = host_threads()
+    ref_ok = False
+    try:
+        from oracle import ref_runner
+        ref_ok = ref_runner.available()
+    except ImportError:
+        pass
+    steps = max(1, args.steps)
+    if ref_ok:
+        per_step = max(2.0, min(15.0, 60.0 / steps))
+        for _ in range(args.warmup):
+            ref_runner.time_strains_dts(1.0, cores)
+        t0 = time.perf_counter()
+        runs = [ref_runner.time_strains_dts(per_step, cores) for _ in range(steps)]
+        elapsed = time.perf_counter() - t0
+        value = float(np.mean([r['value'] for r in runs]))
+        whole = float(np.mean([r['whole_integrate_value'] for r in runs]))
+        members = sum(r['members'] for r in runs) // steps
+        kind = 'reference'
+        sample = ('%d members x 1000 tau-leap steps x 5 compartments per step over %d worker '
+                  'processes, >= %.0f s each, timed inside the workers; unmodified '
+                  'basepop.py:797-852 compiled into oracle/_ref, integrator only'
+                  % (members, cores, per_step))
+        extra = {'whole_integrate_value': whole, 'port': port_baseline(3.0)}
+    else:
+        members, cores = sized_port_sample(2.0)
+        for _ in range(args.warmup):
+            port_arm(max(500, members // 4))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            port_arm(members)
+        elapsed = time.perf_counter() - t0
+        value = steps * members * T_END * 5 / elapsed
+        kind = 'port'
+        sample = ('%d members x %d tau-leap steps x 5 compartments per step, streaming moments, '
+                  'OpenMP over members; C restatement of basepop.py:797-852 '
+                  '(oracle/popdyn_oracle.c)' % (members, T_END))
+        extra = {'note': 'oracle/_ref (the reference\'s own Python loop) did not ship with this '
+                         'run; the pure-Python reference measured 1.09e5 comp-steps/s per core '
+                         '(BASELINE.md)'}
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'comp-steps/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'int64+f64', 'data': 'synthetic',
+        'ms_per_step': 1e3 * elapsed / steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64+f64', 'data': 'synthetic',
         'config': {'workload': workload_name(args.members),
-                   'sample_members_per_step': n_member,
-                   'note': 'each step is a bounded sample of the workload: the oracle port runs '
-                           'sample_members_per_step members with streaming moments'},
-        'cpu_baseline': {'value': value, 'unit': 'comp-steps/s', 'cores': cores, 'kind': 'port',
-                         'sample': sample,
-                         'note': 'C restatement of basepop.py:797-852 (oracle/popdyn_oracle.c); '
-                                 'the pure-Python reference itself measured 1.09e5 comp-steps/s '
-                                 'per core (BASELINE.md)'},
+                   'sample_members_per_step': members,
+                   'note': 'each step is a bounded sample of the workload run by the CPU '
+                           'implementation on all host cores'},
+        'cpu_baseline': dict({'value': value, 'unit': 'comp-steps/s', 'cores': cores,
+                              'kind': kind, 'sample': sample}, **extra),
         'e2e': {'value': value, 'unit': 'comp-steps/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -196,100 +262,181 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def run_gpu_arm(args):
-    import torch
-    import torch.distributed as dist
-    from popdynamics_b200 import capi, compiler, distributed, ensemble
+class Gpu(object):
+    """Process-wide handles of the GPU arm."""
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if world != args.gpus and world > 1:
-        raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback')
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, self.world))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback')
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device('cuda', self.local_rank)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+        self.launches = 0
 
-    M = args.members
-    start = rank * M                      # weak scaling: every rank owns M members
-    model = make_model()
-    model.check_flow_transfers()
-    model.device = local_rank
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, value):
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, value):
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed(self, fn, flush=True):
+        """Device time of fn() in ms (CUDA events on the current stream, L2 flushed before)."""
+        torch = self.torch
+        if flush:
+            self.flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), out
+
+
+def strains_step_fn(g, args, model, cm, M, start, moments, hist, quant):
+    """One pass of the headline hot path over this rank's members [start, start + M)."""
+    from popdynamics_b200 import capi, ensemble
     C, T = len(model.labels), len(model.target_times)
-    cm = compiler.compile_model(model, 'discrete_time_stochastic')
     y = model.get_init_list()
-
-    n_rows = T
-    moments = torch.zeros((T, C, 2), dtype=torch.int64, device=dev)
-    hist = torch.zeros((n_rows, C, HIST_BINS), dtype=torch.int32, device=dev)
-    quant = torch.empty((n_rows, C, len(QUANTILES)), dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     hist_shift = np.zeros(C, dtype=np.int32)
 
-    def one_step(seed):
+    def one_step(seed, count_bits=None):
         moments.zero_()
         hist.zero_()
         res = ensemble.run_compiled(model, cm, 'discrete_time_stochastic', y, model.target_times,
                                     M, output='stats', seed=seed, member_offset=start,
-                                    device=local_rank, count_bits=args.count_bits,
+                                    device=g.local_rank,
+                                    count_bits=count_bits or args.count_bits,
                                     block=args.block, min_blocks=args.min_blocks,
                                     hist_bins=HIST_BINS, hist_max=HIST_MAX,
                                     moments=moments, hist=hist, moments_from=args.moments_from)
         ensemble.raise_device_error(res.info, 'discrete_time_stochastic')
-        if world > 1:
-            dist.all_reduce(hist)
+        if g.world > 1:
+            g.dist.all_reduce(hist)
             if args.moments_from == 'hist':
                 res.derive_moments()              # exact moments of the whole ensemble
             else:
-                dist.all_reduce(moments)
-        capi.hist_quantiles(hist, n_rows, C, HIST_BINS, hist_shift, QUANTILES, quant,
-                            device=local_rank)
+                g.dist.all_reduce(moments)
+        capi.hist_quantiles(hist, T, C, HIST_BINS, hist_shift, QUANTILES, quant,
+                            device=g.local_rank)
         return res
+    return one_step
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+
+def run_headline(g, args):
+    torch = g.torch
+    from popdynamics_b200 import capi, compiler, distributed, ensemble
+
+    M = args.members
+    start = g.rank * M                      # weak scaling: every rank owns M members
+    model = make_model()
+    model.check_flow_transfers()
+    model.device = g.local_rank
+    C, T = len(model.labels), len(model.target_times)
+    cm = compiler.compile_model(model, 'discrete_time_stochastic')
+
+    moments = torch.zeros((T, C, 2), dtype=torch.int64, device=g.dev)
+    hist = torch.zeros((T, C, HIST_BINS), dtype=torch.int32, device=g.dev)
+    quant = torch.empty((T, C, len(QUANTILES)), dtype=torch.int64, device=g.dev)
+    one_step = strains_step_fn(g, args, model, cm, M, start, moments, hist, quant)
 
     for w in range(args.warmup):
         one_step(w)
     peaks, peak_kind = measured_peaks()
-    int_peak = capi.microbench(2, local_rank)        # G int32 op/s (IMAD / LOP3 mix)
-    fp64_peak = capi.microbench(0, local_rank)       # G fp64 op/s (unfused DMUL + DADD)
+    int_peak = capi.microbench(2, g.local_rank)        # G int32 op/s (IMAD.WIDE / LOP3 mix)
+    fp64_peak = capi.microbench(0, g.local_rank)       # G fp64 op/s (unfused DMUL + DADD)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(g.local_rank)
+    if g.rank == 0:
         sampler.start()
-    barrier()
-    step_ms, kernel_ms, draws = [], [], []
+    g.barrier()
+    step_ms, kernel_ms = [], []
     info = None
     t_wall = time.perf_counter()
     for k in range(args.steps):
-        flush.fill_(k & 0xff)                         # evict L2 between timed iterations
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        res = one_step(1000 + k)
-        e1.record()
-        torch.cuda.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
+        ms, res = g.timed(lambda: one_step(1000 + k))       # L2 evicted between timed iterations
+        step_ms.append(ms)
         kernel_ms.append(res.info['kernel_ms'])
         info = res.info
-    barrier()
+    g.barrier()
     wall = time.perf_counter() - t_wall
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if g.rank == 0 else None
+    # per timed step: pd_tau_table_kernel, pd_tau_leap_kernel, pd_hist_moments_kernel,
+    # pd_quantiles_kernel
+    g.launches += 4 * args.steps
 
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    total_ms = g.max_over_ranks(sum(step_ms))
     steps_per_member = T - 1
-    comp_steps_per_step = float(world) * M * steps_per_member * C
+    comp_steps_per_step = float(g.world) * M * steps_per_member * C
     value = comp_steps_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- the same step with 64-bit counts (the reference holds Python ints / numpy.int64) -----
+    one_step(7, count_bits=64)
+    ms64 = [g.timed(lambda: one_step(3000 + k, count_bits=64))[0] for k in range(2)]
+    ms64 = g.max_over_ranks(sum(ms64))
+    value64 = comp_steps_per_step * 2 / (ms64 * 1e-3)
+
+    # ---- strong scaling: 10^7 members in total over the ranks ---------------------------------
+    strong = None
+    total_members = args.strong_members
+    s0, s1 = distributed.shard_range(total_members, g.rank, g.world)
+    if s1 > s0:
+        strong_step = strains_step_fn(g, args, model, cm, s1 - s0, s0, moments, hist, quant)
+        strong_step(11)
+        sms = [g.timed(lambda: strong_step(4000 + k))[0] for k in range(args.steps)]
+        sms = g.max_over_ranks(sum(sms))
+        strong = {'members_total': total_members, 'members_per_gpu': s1 - s0,
+                  'value': float(total_members) * steps_per_member * C * args.steps / (sms * 1e-3),
+                  'unit': 'comp-steps/s', 'ms_per_step': sms / args.steps, 'scaling': 'strong',
+                  'limiter': 'fixed per-step cost: all-reduce of the %.0f MB int32 histograms + '
+                             'pd_hist_moments_kernel + pd_quantiles_kernel'
+                             % (hist.numel() * 4 / 1e6)}
+
+    # ---- N > 1: the reduced statistics must equal a single-GPU run of the same global ids -----
+    multi_check = None
+    if g.world > 1:
+        n_chk = 100000
+        c0, c1 = distributed.shard_range(n_chk, g.rank, g.world)
+        chk = strains_step_fn(g, args, model, cm, c1 - c0, c0, moments, hist, quant)
+        chk(99)
+        reduced_hist, reduced_mom = hist.clone(), moments.clone()
+        if g.rank == 0:
+            saved = g.world
+            g.world = 1                                   # rank 0 alone, no collective
+            try:
+                alone = strains_step_fn(g, args, model, cm, n_chk, 0, moments, hist, quant)
+                alone(99)
+            finally:
+                g.world = saved
+            same = bool(torch.equal(hist, reduced_hist) and torch.equal(moments, reduced_mom))
+            multi_check = {'members': n_chk, 'ranks': g.world, 'identical': same,
+                           'what': 'all-reduced histograms + derived moments of a sharded run '
+                                   'vs rank 0 integrating the same global member ids alone'}
+            if not same:
+                raise SystemExit('multi-GPU statistics differ from the single-GPU run')
+        g.barrier()
 
     # ---- end to end through the public API: HOST inputs (model, initial state, target times)
     # in, HOST statistics (mean, variance, quantiles) out.  statistics='device' keeps the
@@ -297,95 +444,452 @@ def run_gpu_arm(args):
     # for does.
     def e2e_step(seed):
         res = model.integrate_ensemble('discrete_time_stochastic', n_members=M, output='stats',
-                                       seed=seed, member_offset=start, device=local_rank,
+                                       seed=seed, member_offset=start, device=g.local_rank,
                                        count_bits=args.count_bits, block=args.block,
                                        min_blocks=args.min_blocks, statistics='device',
                                        moments_from=args.moments_from,
                                        hist_bins=HIST_BINS, hist_max=HIST_MAX)
-        if world > 1:
-            distributed.allreduce_stats(res, device=dev)
+        if g.world > 1:
+            distributed.allreduce_stats(res, device=g.dev)
+            if args.moments_from == 'hist':
+                res.derive_moments()
         q = res.quantiles(QUANTILES).cpu().numpy()
-        mean, var = res.mean(world * M), res.var(world * M)
+        mean, var = res.mean(g.world * M), res.var(g.world * M)
         out_bytes = q.nbytes + 2 * res.moments.numel() * 8      # quantiles + moments (x2 reads)
         return res, (q, mean, var), out_bytes
 
     e2e_step(0)
-    barrier()
+    g.barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     h2d = d2h = 0
     for k in range(e2e_steps):
         res, _, out_bytes = e2e_step(2000 + k)
         h2d, d2h = res.info['h2d_bytes'], res.info['d2h_bytes'] + out_bytes
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = comp_steps_per_step * e2e_steps / float(e2e_s.item())
+    g.barrier()
+    e2e_s = g.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = comp_steps_per_step * e2e_steps / e2e_s
 
-    if rank == 0:
-        # ---- roofline of the dominant kernel (pd_tau_leap_kernel) ---------------------------
-        k_ms = float(np.mean(kernel_ms))
-        member_steps = float(M) * steps_per_member
-        sm_mhz = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz') or 1965.0
-        issue_peak = SM_COUNT * LANES_PER_SM_PER_CLK * sm_mhz * 1e6 / 1e9      # G thread-inst/s
-        achieved = ALGORITHMIC_OPS_PER_MEMBER_STEP * member_steps / (k_ms * 1e-3) / 1e9
-        useful = USEFUL_INST_PER_MEMBER_STEP * member_steps / (k_ms * 1e-3) / 1e9
-        hbm_peak = peaks.get('hbm_gbs')
-        roofline = {
-            'bound': 'issue', 'kernel': 'pd_tau_leap_kernel',
-            'achieved': achieved, 'peak': issue_peak, 'unit': 'G thread-op/s',
-            'frac': achieved / issue_peak,
-            'frac_executed_useful': useful / issue_peak,
-            'traffic': (DRAM_BYTES_PER_MEMBER_STEP * member_steps
-                        if DRAM_BYTES_PER_MEMBER_STEP is not None else None),
-            'peak_source': '%d SMs x %d lanes/clk x %.0f MHz (median SM clock sampled during the '
-                           'timed region)' % (SM_COUNT, LANES_PER_SM_PER_CLK, sm_mhz),
-            'per_unit': '%.0f algorithmic operations per member-step (SURVEY.md 8d); the kernel '
-                        'executes %.0f useful thread-instructions per member-step (ncu, profiles/)'
-                        % (ALGORITHMIC_OPS_PER_MEMBER_STEP, USEFUL_INST_PER_MEMBER_STEP),
-            'kernel_ms': k_ms, 'share_of_step': k_ms / float(np.mean(step_ms)),
-            'pipe_peaks_gops': {'int32_imad_lop3': int_peak, 'fp64_dmul_dadd': fp64_peak},
-            'hbm': {'algorithmic_bytes_per_member_step': 0.0,
-                    'full_trajectory_bytes_per_member_step': 8.0 * C,
-                    'peak_gbs': hbm_peak, 'peak_kind': peak_kind,
-                    'full_trajectory_ceiling_member_steps_per_s':
-                        (hbm_peak * 1e9 / (8.0 * C)) if hbm_peak else None},
-            'note': 'neither HBM- nor tensor-bound: streaming-statistics mode moves ~0 B per '
-                    'member-step, and even full-trajectory output (8*C B per member-step) has an '
-                    'HBM ceiling ~10x above what the Poisson draws allow; the bound is '
-                    'instruction issue (Philox rounds, fp64 compares, shared-memory bookkeeping)',
-        }
-        cpu_members, cores = sized_cpu_sample(args.cpu_seconds)
-        cpu_value, cpu_dt, cores = cpu_arm(cpu_members)
-        line = {
-            'metric': METRIC, 'value': value, 'unit': 'comp-steps/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'int%d+f64' % args.count_bits, 'data': 'synthetic',
-            'members_per_sec': float(world) * M * args.steps / (total_ms * 1e-3),
-            'config': {'workload': workload_name(M),
-                       'members_per_gpu': M, 'steps_per_member': steps_per_member,
-                       'parallelism': 'members sharded x%d, all-reduce of integer statistics'
-                                      % world,
-                       'l2': 'flushed between timed iterations (256 MiB fill)',
-                       'block': info['block'], 'regs_per_thread': info['regs_per_thread'],
-                       'blocks_per_sm': info['blocks_per_sm']},
-            'roofline': roofline,
-            'cpu_baseline': {'value': cpu_value, 'unit': 'comp-steps/s', 'cores': cores,
-                             'kind': 'port',
-                             'sample': '%d members x 1000 steps x 5 compartments (%.1f s)'
-                                       % (cpu_members, cpu_dt)},
-            'e2e': {'value': e2e_value, 'unit': 'comp-steps/s', 'h2d_bytes_per_step': int(h2d),
-                    'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps},
-            # per timed step: pd_tau_table_kernel, pd_tau_leap_kernel, pd_hist_moments_kernel,
-            # pd_quantiles_kernel
-            'gpu_launches': 4 * args.steps,
-            'clocks': clocks, 'wall_s': wall,
-        }
+    if g.rank != 0:
+        return None
+    # ---- roofline of the dominant kernel (pd_tau_leap_kernel) ---------------------------------
+    k_ms = float(np.mean(kernel_ms))
+    member_steps = float(M) * steps_per_member
+    sm_mhz = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz') or 1965.0
+    issue_peak = SM_COUNT * LANES_PER_SM_PER_CLK * sm_mhz * 1e6 / 1e9      # G thread-inst/s
+    unit = ncu_unit()
+    hbm_peak = peaks.get('hbm_gbs')
+    survey = SURVEY_OPS_PER_MEMBER_STEP * member_steps / (k_ms * 1e-3) / 1e9
+    if unit:
+        useful_per = float(unit['thread_inst_executed_per_member_step'])
+        pred_on_per = float(unit['thread_inst_executed_true_per_member_step'])
+        achieved = useful_per * member_steps / (k_ms * 1e-3) / 1e9
+        frac = achieved / issue_peak
+        frac_pred_on = pred_on_per * member_steps / (k_ms * 1e-3) / 1e9 / issue_peak
+        traffic = float(unit['dram_bytes_per_member_step']) * member_steps
+        per_unit = ('%.0f thread-instructions executed per member-step (active lanes of every '
+                    'issued warp instruction; %.0f with the predicate on), measured by ncu on '
+                    'this kernel (%s, %s); the SURVEY.md 8d estimate of %.0f operations is '
+                    'reported as frac_survey_unit'
+                    % (useful_per, pred_on_per, os.path.relpath(NCU_UNIT_FILE, ROOT),
+                       unit.get('capture', ''), SURVEY_OPS_PER_MEMBER_STEP))
+    else:
+        achieved, frac, traffic, frac_pred_on = None, None, None, None
+        per_unit = 'no ncu capture committed for this build (%s missing)' \
+            % os.path.relpath(NCU_UNIT_FILE, ROOT)
+    roofline = {
+        'bound': 'issue', 'kernel': 'pd_tau_leap_kernel',
+        'achieved': achieved, 'peak': issue_peak, 'unit': 'G thread-inst/s',
+        'frac': frac, 'frac_pred_on': frac_pred_on, 'frac_survey_unit': survey / issue_peak,
+        'ncu': ({k: unit.get(k) for k in ('issue_active_pct', 'lanes_per_inst',
+                                          'frac_issue_x_lanes', 'pipe_fmaheavy_pct',
+                                          'warp_inst_per_unit')} if unit else None),
+        'traffic': traffic,
+        'peak_source': '%d SMs x %d lanes/clk x %.0f MHz (median SM clock sampled during the '
+                       'timed region)' % (SM_COUNT, LANES_PER_SM_PER_CLK, sm_mhz),
+        'per_unit': per_unit,
+        'kernel_ms': k_ms, 'share_of_step': k_ms / float(np.mean(step_ms)),
+        'pipe_peaks_gops': {'int32_imad_wide_lop3': int_peak, 'fp64_dmul_dadd': fp64_peak},
+        'hbm': {'algorithmic_bytes_per_member_step': 0.0,
+                'full_trajectory_bytes_per_member_step': 8.0 * C,
+                'peak_gbs': hbm_peak, 'peak_kind': peak_kind,
+                'full_trajectory_ceiling_member_steps_per_s':
+                    (hbm_peak * 1e9 / (8.0 * C)) if hbm_peak else None},
+        'note': 'neither HBM- nor tensor-bound: streaming-statistics mode moves ~0 B per '
+                'member-step, and even full-trajectory output (8*C B per member-step) has an '
+                'HBM ceiling ~10x above what the Poisson draws allow; the bound is instruction '
+                'issue, and inside it the FMA-heavy pipe: IMAD.WIDE.U32 (two per Philox round) '
+                'issues once per 4 cycles per scheduler on B200 (pd_microbench kinds 2-4)',
+    }
+    cpu = port_baseline(args.cpu_seconds)
+    try:
+        ref = reference_python_baseline(min(6.0, args.cpu_seconds))
+    except Exception as exc:                                   # pragma: no cover
+        ref = {'unavailable': str(exc)}
+    if ref:
+        cpu['reference_python'] = ref
+    return {
+        'metric': METRIC, 'value': value, 'unit': 'comp-steps/s', 'n_gpus': g.world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'int%d+f64' % args.count_bits, 'data': 'synthetic',
+        'members_per_sec': float(g.world) * M * args.steps / (total_ms * 1e-3),
+        'value_count_bits_64': value64,
+        'config': {'workload': workload_name(M),
+                   'members_per_gpu': M, 'steps_per_member': steps_per_member,
+                   'parallelism': 'members sharded x%d, all-reduce of integer statistics'
+                                  % g.world,
+                   'l2': 'flushed between timed iterations (256 MiB fill)',
+                   'block': info['block'], 'regs_per_thread': info['regs_per_thread'],
+                   'blocks_per_sm': info['blocks_per_sm']},
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+        'e2e': {'value': e2e_value, 'unit': 'comp-steps/s', 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps},
+        'strong_scaling': strong,
+        'multi_gpu_check': multi_check,
+        'clocks': clocks, 'wall_s': wall,
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations
+# ---------------------------------------------------------------------------------------------
+def golden():
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_vectors.npz'))
+
+
+def oracle_explicit_rate(model_fn, n_sample, seconds_hint):
+    """Oracle port (CPU baseline leg) on a bounded sample of an explicit sweep."""
+    from oracle import oracle
+    from popdynamics_b200 import compiler
+    model = model_fn(0, n_sample)
+    model.check_flow_transfers()
+    cm = compiler.compile_model(model, 'explicit')
+    om = oracle.OracleModel(cm)
+    cores = host_threads()
+    t0 = time.perf_counter()
+    out = om.explicit_batch(n_sample, model.get_init_list(), model.target_times,
+                            want_soln=False, n_thread=cores)
+    dt = time.perf_counter() - t0
+    steps = out['n_steps']
+    return {'value': steps * cm.n_comp / dt, 'unit': 'comp-steps/s', 'cores': cores,
+            'kind': 'port', 'steps_per_s': steps / dt,
+            'sample': '%d members of the same sweep, full length (%.1f s)' % (n_sample, dt)}
+
+
+def explicit_sweep_config(g, args, name, model_fn, total_members, ops_key, want_var, check):
+    """An explicit-Euler parameter sweep over the N ranks: device-timed with resident inputs,
+    then end to end through BaseModel.integrate_ensemble with HOST parameter columns."""
+    torch = g.torch
+    from popdynamics_b200 import capi, compiler, distributed, ensemble
+    s0, s1 = distributed.shard_range(total_members, g.rank, g.world)
+    M = s1 - s0
+    model = model_fn(s0, s1)
+    model.device = g.local_rank
+    model.check_flow_transfers()
+    cm = compiler.compile_model(model, 'explicit')
+    C = cm.n_comp
+    y = model.get_init_list()
+    rows = ensemble._member_param_rows(cm, M)
+    mp = torch.stack([torch.from_numpy(r) for r in rows]).to(g.dev)
+    out = torch.empty((C, M), dtype=torch.float64, device=g.dev)
+
+    def device_step():
+        res = ensemble.run_compiled(model, cm, 'explicit', y, model.target_times, M,
+                                    output='final', device=g.local_rank, member_params=mp, out=out)
+        ensemble.raise_device_error(res.info, 'explicit')
+        return res
+    device_step()
+    g.barrier()
+    ms, res = g.timed(device_step)
+    ms = g.max_over_ranks(ms)
+    g.launches += 1
+    steps_per_member = int(res.info['n_steps']) // M
+    total_steps = float(total_members) * steps_per_member
+    value = total_steps * C / (ms * 1e-3)
+    kernel_ms = res.info['kernel_ms']
+    del mp, out
+    torch.cuda.empty_cache()
+
+    # end to end: host parameter columns in (chunked, double-buffered inside the C-ABI), host
+    # result out -- the final state, or one diagnostic var per member
+    def e2e_step():
+        r = model.integrate_ensemble('explicit', n_members=M, output='final',
+                                     device=g.local_rank,
+                                     out=(torch.empty((C, M), dtype=torch.float64, device=g.dev)
+                                          if want_var else None))
+        moved = [r.info['h2d_bytes'], r.info['d2h_bytes']]
+        if want_var:
+            host = np.empty((1, M), dtype=np.float64)
+            d = ensemble.diagnostics(model, r, want_vars=[want_var], out=host)
+            moved[0] += d.info['h2d_bytes']
+            moved[1] += d.info['d2h_bytes']
+            return r, host[0], moved, r.info['n_launch']
+        return r, r.final, moved, r.info['n_launch']
+    g.barrier()
+    t0 = time.perf_counter()
+    r, host_out, moved, n_chunk = e2e_step()
+    g.barrier()
+    e2e_s = g.max_over_ranks(time.perf_counter() - t0)
+    g.launches += n_chunk + (1 if want_var else 0)
+    parity = check(s0, s1, r, host_out) if g.rank == 0 else None
+    del r
+    torch.cuda.empty_cache()
+    if g.rank != 0:
+        return None
+    fp64_peak = capi.microbench(0, g.local_rank)
+    ops = EXPLICIT_OPS[ops_key]
+    achieved = ops * (float(M) * steps_per_member) / (kernel_ms * 1e-3) / 1e9
+    return {
+        'config': name, 'n_gpus': g.world, 'scaling': 'strong', 'members_total': total_members,
+        'members_per_gpu': M, 'steps_per_member': steps_per_member, 'compartments': C,
+        'ms': ms, 'value': value, 'unit': 'comp-steps/s', 'steps_per_s': total_steps / (ms * 1e-3),
+        'members_per_sec': total_members / (ms * 1e-3),
+        'dtype': 'f64', 'data': 'synthetic',
+        'e2e': {'value': total_steps * C / e2e_s, 'unit': 'comp-steps/s',
+                'h2d_bytes_per_step': int(moved[0]), 'd2h_bytes_per_step': int(moved[1]),
+                'seconds': e2e_s, 'chunks': n_chunk, 'over_device_value': (total_steps * C / e2e_s) / value},
+        'roofline': {'bound': 'fp64 pipe', 'kernel': 'pd_explicit_kernel',
+                     'achieved': achieved, 'peak': fp64_peak, 'unit': 'G fp64 op/s',
+                     'frac': achieved / fp64_peak, 'traffic': None,
+                     'per_unit': '%.0f fp64 operations per derivative evaluation (SURVEY.md 8d), '
+                                 'unfused (--fmad=false); peak = pd_microbench DMUL+DADD on this '
+                                 'GPU' % ops},
+        'parity': parity,
+    }
+
+
+def config_seir(g, args):
+    from examples import configs
+    gold = golden()[configs.SEIR_GOLDEN_KEY]
+
+    def check(s0, s1, r, final):
+        got = np.asarray(final)[:, 0]
+        ok = bool(np.array_equal(got, gold))
+        if not ok:
+            raise SystemExit('config 2: member 0 differs from the reference golden: %r vs %r'
+                             % (got, gold))
+        return {'what': 'member 0 (measles base case) equals the unmodified reference\'s '
+                        '18 250-day final state bit for bit (tests/golden, key %s)'
+                        % configs.SEIR_GOLDEN_KEY, 'ok': ok}
+    line = explicit_sweep_config(
+        g, args, '2: SEIR-demography sweep (r0, duration_infectious, duration_preinfectious), '
+        'explicit Euler, make_times(0, 18250, 1)', configs.seir_sweep, args.seir_members,
+        'seir', None, check)
+    if line is not None:
+        line['cpu_baseline'] = oracle_explicit_rate(configs.seir_sweep, 16 * host_threads(), 3)
+    return line
+
+
+def config_rmit(g, args):
+    from examples import configs
+    gold = golden()['rmit_fig2_proportion']
+
+    def check(s0, s1, r, proportion):
+        n = min(len(gold), s1 - s0) if s0 == 0 else 0
+        ok = bool(np.array_equal(np.asarray(proportion)[:n], gold[:n]))
+        if not ok:
+            raise SystemExit('config 5: embedded golden members differ: %r vs %r'
+                             % (np.asarray(proportion)[:n], gold[:n]))
+        finite = bool(np.isfinite(np.asarray(proportion)).all())
+        return {'what': 'members 0..5 (six beta points of the reference\'s figure 2) equal '
+                        'model.vars[\'proportion\'] of the unmodified reference bit for bit '
+                        '(tests/golden, key rmit_fig2_proportion); every proportion finite',
+                'ok': ok and finite}
+    line = explicit_sweep_config(
+        g, args, '5: RMIT TB calibration sweep (beta, rho, sigma1..3), explicit Euler, '
+        'make_times(0, 500, 1), output = vars[\'proportion\'] of the final state per member',
+        configs.rmit_sweep, args.rmit_members, 'rmit', 'proportion', check)
+    if line is not None:
+        line['cpu_baseline'] = oracle_explicit_rate(configs.rmit_sweep, 1024 * host_threads(), 3)
+    return line
+
+
+def config_tb(g, args):
+    """Config 4: the TB model under Gillespie for 50 simulated years; members scale with N
+    (125 000 per GPU: the stated 10^6 on 8 GPUs -- about 5.5e6 events per member)."""
+    from examples import configs
+    from oracle import oracle
+    from popdynamics_b200 import capi, compiler, ensemble
+    torch = g.torch
+    M = args.tb_members
+    start = g.rank * M
+    method = 'continuous_time_stochastic'
+    warm = configs.tb_gillespie()
+    warm.device = g.local_rank
+    warm.make_times(1950, 1950.01, 0.01)                  # NVRTC compile + module load
+    warm.integrate_ensemble(method, n_members=256, output='final', seed=0, count_bits=32,
+                            device=g.local_rank)
+    model = configs.tb_gillespie()
+    model.device = g.local_rank
+    g.barrier()
+    t0 = time.perf_counter()
+    res = model.integrate_ensemble(method, n_members=M, output='final', seed=0,
+                                   member_offset=start, count_bits=32, device=g.local_rank)
+    g.barrier()
+    wall = g.max_over_ranks(time.perf_counter() - t0)
+    ms = g.max_over_ranks(res.info['kernel_ms'])
+    events = g.sum_over_ranks(res.info['n_steps'])
+    g.launches += 1
+    final = np.asarray(res.final)
+    mean_pop = g.sum_over_ranks(final.sum()) / (g.world * M)
+    if g.rank != 0:
+        return None
+    C = final.shape[0]
+    cm = compiler.compile_model(model, method)
+    # CPU baseline leg: the oracle port, one member per host core, the full 50 years
+    cores = host_threads()
+    om = oracle.OracleModel(cm)
+    t0 = time.perf_counter()
+    out = om.stochastic_batch(method, cores, model.get_init_list(), model.target_times, seed=0,
+                              want_soln=False, n_thread=cores)
+    dt = time.perf_counter() - t0
+    S = cm.n_flow
+    ops_per_event = 11 + 1 + 2 * S + 7 * S + 50       # vars, rates, cumsum, Neumaier sum, log/div
+    fp64_peak = capi.microbench(0, g.local_rank)
+    achieved = ops_per_event * (res.info['n_steps'] / (res.info['kernel_ms'] * 1e-3)) / 1e9
+    return {
+        'config': '4: TB model (scale-ups evaluated in the loop), Gillespie direct method, '
+                  'make_times(1950, 2000, 1), population 1e6',
+        'n_gpus': g.world, 'scaling': 'weak', 'members_total': g.world * M,
+        'members_per_gpu': M, 'events': events, 'events_per_member': events / (g.world * M),
+        'ms': ms, 'value': events / (ms * 1e-3), 'unit': 'events/s',
+        'comp_steps_per_s': events * C / (ms * 1e-3),
+        'members_per_sec': g.world * M / (ms * 1e-3), 'dtype': 'int32+f64', 'data': 'synthetic',
+        'note': '125 000 members per GPU by default: the stated 10^6 members on 8 GPUs',
+        'e2e': {'value': events / wall, 'unit': 'events/s',
+                'h2d_bytes_per_step': int(res.info['h2d_bytes']),
+                'd2h_bytes_per_step': int(res.info['d2h_bytes']), 'seconds': wall},
+        'roofline': {'bound': 'issue / fp64 pipe', 'kernel': 'pd_gillespie_kernel',
+                     'achieved': achieved, 'peak': fp64_peak, 'unit': 'G fp64 op/s',
+                     'frac': achieved / fp64_peak, 'traffic': None,
+                     'regs_per_thread': res.info['regs_per_thread'],
+                     'blocks_per_sm': res.info['blocks_per_sm'],
+                     'per_unit': '%d fp64 operations per event (11 vars + %d rates + %d cumulative '
+                                 'adds + 7 x %d compensated-sum operations + ~50 for log and '
+                                 'divide)' % (ops_per_event, S, S, S)},
+        'cpu_baseline': {'value': out['n_steps'] / dt, 'unit': 'events/s', 'cores': cores,
+                         'kind': 'port',
+                         'sample': '%d members x 50 years (%.1f s)' % (cores, dt)},
+        'parity': {'what': 'no member raised the device error flag; mean final population '
+                           '%.6g (deterministic model: 1.49e6); bit-exact comparison with the '
+                           'oracle is in tests/test_gpu_configs.py' % mean_pop,
+                   'ok': bool(res.info['err_code'] == 0 and 1.3e6 < mean_pop < 1.7e6)},
+    }
+
+
+def config_hybrid(g, args):
+    """Config 5b: mix_model.py's day-by-day switching between Gillespie and explicit Euler."""
+    from examples import configs
+    from popdynamics_b200 import ensemble
+    torch = g.torch
+    M = args.hybrid_members
+    model = configs.mix_model()
+    model.device = g.local_rank
+    ensemble.integrate_hybrid(model, configs.MIX_SEGMENTS[:3], 4096, configs.MIX_CUTOFF,
+                              seed=1, device=g.local_rank)                       # warm-up / NVRTC
+    g.barrier()
+    t0 = time.perf_counter()
+    res = ensemble.integrate_hybrid(model, configs.MIX_SEGMENTS, M, configs.MIX_CUTOFF, seed=5,
+                                    member_offset=g.rank * M, device=g.local_rank)
+    torch.cuda.synchronize()
+    g.barrier()
+    wall = g.max_over_ranks(time.perf_counter() - t0)
+    launches = res.info.get('launches', [])
+    g.launches += len(launches)
+    kernel_ms = sum(l['kernel_ms'] for l in launches)
+    final = res.final
+    conserved = bool((final.sum(dim=0) - 100.0).abs().max().item() < 1e-9)
+    explicit_share = float(res.modes.float().mean().item())
+    if g.rank != 0:
+        return None
+    return {
+        'config': '5b: mix_model.py SIR (population 100), 50 one-day segments of step 0.2, '
+                  'Gillespie while min(compartments) <= 3 else explicit Euler',
+        'n_gpus': g.world, 'scaling': 'weak', 'members_total': g.world * M, 'members_per_gpu': M,
+        'ms': wall * 1e3, 'kernel_ms_sum': kernel_ms, 'launches': len(launches),
+        'value': g.world * M / wall, 'unit': 'members/s', 'dtype': 'int64+f64',
+        'data': 'synthetic',
+        'e2e': {'value': g.world * M / wall, 'unit': 'members/s', 'h2d_bytes_per_step': 24,
+                'd2h_bytes_per_step': 0, 'seconds': wall},
+        'roofline': None,
+        'parity': {'what': 'closed population conserved for every member; share of '
+                           '(member, segment) pairs integrated explicitly %.3f; per-member '
+                           'bit-exact comparison with the oracle loop is in '
+                           'tests/test_gpu_configs.py' % explicit_share,
+                   'ok': conserved},
+    }
+
+
+def config_adaptive(g, args):
+    """Config 6: the adaptive solver behind integrate('scipy') on the SEIR-demography sweep."""
+    from examples import configs
+    from popdynamics_b200 import capi, distributed
+    if 'scipy' not in capi.METHOD_CODES:
+        return None
+    total = args.adaptive_members
+    s0, s1 = distributed.shard_range(total, g.rank, g.world)
+    model = configs.seir_sweep(s0, s1)
+    model.device = g.local_rank
+    model.integrate_ensemble('scipy', n_members=min(4096, s1 - s0), output='final',
+                             device=g.local_rank) if s1 - s0 > 4096 else None
+    g.barrier()
+    t0 = time.perf_counter()
+    res = model.integrate_ensemble('scipy', n_members=s1 - s0, output='final',
+                                   device=g.local_rank)
+    g.barrier()
+    wall = g.max_over_ranks(time.perf_counter() - t0)
+    ms = g.max_over_ranks(res.info['kernel_ms'])
+    steps = g.sum_over_ranks(res.info['n_steps'])
+    g.launches += res.info['n_launch']
+    if g.rank != 0:
+        return None
+    gold = golden()
+    parity = None
+    if 'seird_odeint_18250_final' in gold.files:
+        got = np.asarray(res.final)[:, 0]
+        want = gold['seird_odeint_18250_final']
+        rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)))
+        parity = {'what': 'member 0 vs the unmodified reference\'s integrate(\'scipy\') '
+                          '(scipy odeint, LSODA) final state: max relative difference %.2e '
+                          '(tolerance 1e-5, DESIGN.md)' % rel, 'ok': rel < 1e-5}
+    return {
+        'config': '6: SEIR-demography sweep through the adaptive Dormand-Prince 5(4) solver '
+                  '(integrate(\'scipy\') equivalent), make_times(0, 18250, 1)',
+        'n_gpus': g.world, 'scaling': 'strong', 'members_total': total,
+        'ms': ms, 'value': steps / (ms * 1e-3), 'unit': 'accepted+rejected steps/s',
+        'steps_per_member': steps / total, 'members_per_sec': total / (ms * 1e-3),
+        'dtype': 'f64', 'data': 'synthetic',
+        'e2e': {'value': steps / wall, 'unit': 'steps/s',
+                'h2d_bytes_per_step': int(res.info['h2d_bytes']),
+                'd2h_bytes_per_step': int(res.info['d2h_bytes']), 'seconds': wall},
+        'roofline': None, 'parity': parity,
+    }
+
+
+def run_gpu_arm(args):
+    g = Gpu(args)
+    line = run_headline(g, args)
+    configs = []
+    if args.configs != 'headline':
+        wanted = ['seir', 'tb', 'rmit', 'hybrid', 'adaptive'] if args.configs == 'all' \
+            else args.configs.split(',')
+        table = {'seir': config_seir, 'tb': config_tb, 'rmit': config_rmit,
+                 'hybrid': config_hybrid, 'adaptive': config_adaptive}
+        for name in wanted:
+            t0 = time.perf_counter()
+            entry = table[name](g, args)
+            g.barrier()
+            if g.rank == 0 and entry is not None:
+                entry['bench_wall_s'] = time.perf_counter() - t0
+                configs.append(entry)
+    if g.rank == 0:
+        line['configs'] = configs
+        line['gpu_launches'] = g.launches
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if g.world > 1:
+        g.dist.destroy_process_group()
 
 
 def main():
@@ -394,7 +898,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--members', type=int, default=10**7, help='members per GPU')
+    ap.add_argument('--members', type=int, default=10**7, help='members per GPU (weak scaling)')
+    ap.add_argument('--strong-members', type=int, default=10**7,
+                    help='members in total for the strong-scaling figure')
     ap.add_argument('--count-bits', type=int, default=32, choices=[32, 64],
                     help='width of the integer counts (32: overflow raises the device error flag)')
     ap.add_argument('--min-blocks', type=int, default=4, help='__launch_bounds__ resident-block cap')
@@ -403,6 +909,13 @@ def main():
                     help="'hist': exact moments derived from the width-1 histograms after the "
                          "launch; 'kernel': reduced inside the integrator kernel")
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--configs', default='all',
+                    help="'all', 'headline', or a comma list of seir,tb,rmit,hybrid,adaptive")
+    ap.add_argument('--seir-members', type=int, default=10**6, help='config 2, in total')
+    ap.add_argument('--rmit-members', type=int, default=10**8, help='config 5, in total')
+    ap.add_argument('--tb-members', type=int, default=125000, help='config 4, per GPU')
+    ap.add_argument('--hybrid-members', type=int, default=1 << 20, help='config 5b, per GPU')
+    ap.add_argument('--adaptive-members', type=int, default=10**6, help='config 6, in total')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

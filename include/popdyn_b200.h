@@ -15,6 +15,14 @@
  * functions return 0 on success or a negative pd_status; pd_last_error() gives the message of
  * the calling thread's last failure.  Handles are thread-compatible, not thread-safe.  There is
  * no CPU fallback: without a CUDA device the run functions fail with PD_E_NO_DEVICE.
+ *
+ * Staging of HOST per-member buffers (y0 [C][M], member_params, soln / final_state, mask): when
+ * they add up to more than about 192 MB the member range is cut into chunks that flow through
+ * two streams -- H2D(c+1) and D2H(c-1) overlap the kernel of chunk c -- with one
+ * cudaMemcpy2DAsync per buffer per chunk, so a 10^8-member sweep never needs its inputs resident
+ * at once and the copies hide behind the integration.  pd_run_result.n_launch is the number of
+ * chunks; kernel_ms is then the span of the pipelined region.  Events, the error block and the
+ * staging scratch are kept by the handle between runs (nothing is created per call).
  */
 #ifndef POPDYN_B200_H
 #define POPDYN_B200_H
@@ -112,6 +120,10 @@ typedef struct {
                                      pd_hist_moments on the (lossless) histograms afterwards:
                                      needs hist at every target time with hist_shift == 0; a
                                      count in the last bin raises the device error flag         */
+  const double *const *member_param_rows; /* [n_member_param] HOST array of row pointers, each to
+                                     [M] doubles (host or device): the swept parameter columns as
+                                     the caller holds them, instead of one [P][M] block; used when
+                                     member_params is NULL                                      */
 } pd_stoch_run;
 
 typedef struct {
@@ -129,6 +141,7 @@ typedef struct {
   void *stream;
   const uint8_t *mask;            /* as in pd_stoch_run                                       */
   int32_t mask_value, reserved;
+  const double *const *member_param_rows; /* as in pd_stoch_run                                */
 } pd_explicit_run;
 
 /* The diagnostics pass over stored trajectories (model built with method PD_DIAGNOSTICS, the
@@ -144,6 +157,7 @@ typedef struct {
   double *var_soln;               /* [T][n_var][M]                                             */
   double *flow_soln;              /* [T][C][M] or NULL                                         */
   void *stream;
+  const double *const *member_param_rows; /* as in pd_stoch_run                                */
 } pd_diag_run;
 
 /* ---- library ---------------------------------------------------------------------------- */

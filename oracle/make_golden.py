@@ -63,6 +63,12 @@ def main():
     m = seir['SeirDemographyModel'](SEIR['measles']); m.make_times(0, 2000, 1)
     m.integrate('explicit')
     out['seird_explicit_2000'] = m.soln_array
+    # BASELINE config 2 at its stated length: 50 years, 376 696 derivative evaluations
+    # (examples/seir_model.py:458-464); rows every 365 days plus the final state
+    m = seir['SeirDemographyModel'](SEIR['measles']); m.make_times(0, 365 * 50, 1)
+    m.integrate('explicit')
+    out['seird_explicit_18250_every365'] = m.soln_array[::365]
+    out['seird_explicit_18250_final'] = m.soln_array[-1]
     for tag, interventions in (('tb', []), ('tb_vacc', ['vaccination'])):
         m = tb(interventions); m.make_times(1900, 2050, .05); m.integrate(method='explicit')
         out[tag + '_explicit_every50'] = m.soln_array[::50]
@@ -74,14 +80,26 @@ def main():
     out['rmit_explicit'] = m.soln_array
     out['rmit_proportion'] = np.array([m.vars['proportion']])
     betas = [1., 7., 20., 99., 250., 500.]
-    props = []
+    props, vals = [], []
     for beta in betas:
         m = rmit(dict(RMIT, sigma1=0.25, sigma2=0.125, sigma3=0.125, tau=2.))
         m.set_param('beta', beta); m.set_param('rho', 0.5); m.make_times(0, 500., 1.)
         m.integrate(method='explicit')
         props.append(m.soln_array[-1])
+        vals.append(m.vars['proportion'])
     out['rmit_sweep_betas'] = np.array(betas)
     out['rmit_sweep_final'] = np.array(props)
+    out['rmit_sweep_proportion'] = np.array(vals)   # model.vars['proportion'], rmit_tb_model.py:143
+    # figure 2 of the RMIT example (rmit_tb_model.py:133-143): sigma = 0, beta swept, the value
+    # read is model.vars['proportion'] of the final state -- six of its beta points
+    finals, vals = [], []
+    for beta in betas:
+        m = rmit(RMIT); m.set_param('beta', float(beta)); m.make_times(0, 500., 1.)
+        m.integrate(method='explicit')
+        finals.append(m.soln_array[-1]); vals.append(m.vars['proportion'])
+    out['rmit_fig2_betas'] = np.array(betas)
+    out['rmit_fig2_final'] = np.array(finals)
+    out['rmit_fig2_proportion'] = np.array(vals)
     m = strains(); m.make_times(0, 200, 1); m.integrate('explicit')
     out['strains_explicit'] = m.soln_array
 

@@ -99,12 +99,53 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+# opcode numbering of the oracle's bytecode interpreter (oracle/popdyn_oracle.h)
+OPS = ('const', 'add', 'sub', 'mul', 'div', 'neg', 'fabs', 'floor', 'lt', 'le', 'gt', 'ge',
+       'eq', 'ne', 'and', 'or', 'not', 'isfinite', 'select', 'exp')
+OPCODE = {name: i for i, name in enumerate(OPS)}
+
+
+def oracle_program(cm):
+    """The traced expression graph of a ``CompiledModel`` as the bytecode the C oracle
+    interprets.  Value slots: [compartments | parameters | time | scale-ups | one per
+    instruction]; instructions in the graph's evaluation order (program order of the hook)."""
+    g = cm.graph
+    C, NP, NSU = cm.n_comp, cm.n_param, cm.n_su
+    base = C + NP + 1 + NSU
+    slot_of, ins, consts = {}, [], []
+    for n in cm.order:
+        node = g.nodes[n]
+        op = node[0]
+        if op == 'comp':
+            slot_of[n] = node[1]
+        elif op == 'param':
+            slot_of[n] = C + node[1]
+        elif op == 'time':
+            slot_of[n] = C + NP
+        elif op == 'su':
+            slot_of[n] = C + NP + 1 + node[1]
+        elif op == 'const':
+            consts.append(g.const_values[n])
+            slot_of[n] = base + len(ins)
+            ins.append((OPCODE['const'], len(consts) - 1, -1, -1))
+        else:
+            args = [slot_of[x] if x >= 0 else -1 for x in node[1:]]
+            slot_of[n] = base + len(ins)
+            ins.append((OPCODE[op], args[0], args[1], args[2]))
+    return dict(
+        ins=np.asarray(ins, dtype=np.int32).reshape(-1, 4),
+        consts=np.asarray(consts, dtype=np.float64),
+        slot=np.asarray([slot_of[n] for n in cm.flow_node], dtype=np.int32),
+        check=np.asarray([slot_of[n] for n in cm.check_nodes], dtype=np.int32),
+        n_values=base + len(ins), slot_of=slot_of)
+
+
 class OracleModel(object):
     """A ``CompiledModel`` (popdynamics_b200.compiler) handed to the C oracle."""
 
     def __init__(self, cm):
         self.cm = cm
-        prog = cm.oracle_program()
+        prog = oracle_program(cm)
         table = cm.flow_table()
         self._keep = dict(ins=np.ascontiguousarray(prog['ins']), consts=prog['consts'],
                           kind=table['kind'], frm=table['frm'], to=table['to'],

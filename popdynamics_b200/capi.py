@@ -82,7 +82,7 @@ class StochRun(C.Structure):
                 ('hist', C.c_void_p), ('hist_row', C.c_void_p), ('hist_shift', C.c_void_p),
                 ('hist_bins', C.c_int32), ('n_hist_row', C.c_int32), ('stream', C.c_void_p),
                 ('mask', C.c_void_p), ('mask_value', C.c_int32),
-                ('moments_from_hist', C.c_int32)]
+                ('moments_from_hist', C.c_int32), ('member_param_rows', C.c_void_p)]
 
 
 class ExplicitRun(C.Structure):
@@ -92,7 +92,8 @@ class ExplicitRun(C.Structure):
                 ('n_sub', C.c_void_p), ('dt', C.c_void_p), ('t_eval', C.c_void_p),
                 ('scaleup_table', C.c_void_p), ('n_steps', C.c_int64),
                 ('soln', C.c_void_p), ('final_state', C.c_void_p), ('stream', C.c_void_p),
-                ('mask', C.c_void_p), ('mask_value', C.c_int32), ('reserved', C.c_int32)]
+                ('mask', C.c_void_p), ('mask_value', C.c_int32), ('reserved', C.c_int32),
+                ('member_param_rows', C.c_void_p)]
 
 
 class DiagRun(C.Structure):
@@ -100,7 +101,8 @@ class DiagRun(C.Structure):
                 ('soln', C.c_void_p), ('uniform_params', C.c_void_p),
                 ('member_params', C.c_void_p), ('times', C.c_void_p),
                 ('scaleup_row', C.c_void_p), ('var_soln', C.c_void_p),
-                ('flow_soln', C.c_void_p), ('stream', C.c_void_p)]
+                ('flow_soln', C.c_void_p), ('stream', C.c_void_p),
+                ('member_param_rows', C.c_void_p)]
 
 
 _lib = None
@@ -163,6 +165,13 @@ def address(buf):
             raise ValueError('tensor must be contiguous')
         return buf.data_ptr()
     raise TypeError('expected numpy.ndarray or torch.Tensor, got %s' % type(buf).__name__)
+
+
+def row_pointers(buffers):
+    """HOST array of row addresses for ``member_param_rows``: one pointer per swept parameter
+    column (numpy or torch, each [M] float64).  Returns (keep-alive object, address)."""
+    table = (C.c_void_p * len(buffers))(*[address(b) for b in buffers])
+    return table, C.addressof(table)
 
 
 def device_count():

@@ -13,8 +13,8 @@ Lowers a ``BaseModel`` (popdynamics_b200/basepop.py; reference /root/reference/b
   re-associated, so the device evaluates exactly the reference's arithmetic (kernels are built
   with ``--fmad=false``).
 
-The DAG is emitted twice: as CUDA C for NVRTC (``cuda_source``) and as a tiny bytecode that the
-CPU oracle interprets (``oracle_program``; tests only).  Python constructs that cannot be lowered
+The DAG is emitted as CUDA C for NVRTC (``cuda_source``); the CPU oracle builds its own bytecode
+from the same graph in oracle/oracle.py (test infrastructure).  Python constructs that cannot be lowered
 (``bool()`` of a traced value, ``math.*`` on it, ``int()``/``float()``, ``**``, numpy ufuncs) raise
 ``TraceError`` -- nothing is silently run on the CPU.
 """
@@ -32,10 +32,9 @@ import numpy
 ENTRY, VAR, FIXED, BGDEATH, INFDEATH = 0, 1, 2, 3, 4
 KIND_NAMES = ('entry', 'var', 'fixed', 'bgdeath', 'infdeath')
 
-# opcode numbering shared with oracle/popdyn_oracle.h
+# node operations of the expression graph
 OPS = ('const', 'add', 'sub', 'mul', 'div', 'neg', 'fabs', 'floor', 'lt', 'le', 'gt', 'ge',
        'eq', 'ne', 'and', 'or', 'not', 'isfinite', 'select', 'exp')
-OPCODE = {name: i for i, name in enumerate(OPS)}
 _BOOL_OPS = frozenset(('lt', 'le', 'gt', 'ge', 'eq', 'ne', 'and', 'or', 'not', 'isfinite'))
 
 
@@ -455,38 +454,6 @@ class CompiledModel(object):
         return dict(kind=as_i32(self.flow_kind), frm=as_i32(self.flow_from),
                     to=as_i32(self.flow_to), is_int=as_i32(self.flow_is_int))
 
-    # ---- oracle bytecode (tests only consume it; building it is plain host logic) ----------
-    def oracle_program(self):
-        g = self.graph
-        C, NP, NSU = self.n_comp, self.n_param, self.n_su
-        base = C + NP + 1 + NSU
-        slot_of, ins, consts = {}, [], []
-        for n in self.order:
-            node = g.nodes[n]
-            op = node[0]
-            if op == 'comp':
-                slot_of[n] = node[1]
-            elif op == 'param':
-                slot_of[n] = C + node[1]
-            elif op == 'time':
-                slot_of[n] = C + NP
-            elif op == 'su':
-                slot_of[n] = C + NP + 1 + node[1]
-            elif op == 'const':
-                consts.append(g.const_values[n])
-                slot_of[n] = base + len(ins)
-                ins.append((OPCODE['const'], len(consts) - 1, -1, -1))
-            else:
-                args = [slot_of[x] if x >= 0 else -1 for x in node[1:]]
-                slot_of[n] = base + len(ins)
-                ins.append((OPCODE[op], args[0], args[1], args[2]))
-        return dict(
-            ins=numpy.asarray(ins, dtype=numpy.int32).reshape(-1, 4),
-            consts=numpy.asarray(consts, dtype=numpy.float64),
-            slot=numpy.asarray([slot_of[n] for n in self.flow_node], dtype=numpy.int32),
-            check=numpy.asarray([slot_of[n] for n in self.check_nodes], dtype=numpy.int32),
-            n_values=base + len(ins), slot_of=slot_of)
-
     # ---- CUDA C for NVRTC ------------------------------------------------------------------
     def cuda_source(self):
         from .codegen import emit_model_header
@@ -531,7 +498,8 @@ class _Tracer(object):
         return self.param_symbol('<%s>' % tag, value)
 
 
-def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=False):
+def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=False,
+                  want_vars=None):
     """Lower ``model`` for ``method`` ('explicit', 'discrete_time_stochastic',
     'continuous_time_stochastic').  ``model.set_flows()`` must already have run
     (``check_flow_transfers``, basepop.py:638-656).
@@ -541,7 +509,9 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
     of ``soln_array`` -- floats whatever the integrator was, so ``old_div`` divides truly and
     ``sum`` folds naively -- then ``calculate_vars``, ``calculate_flows`` and the
     ``calculate_diagnostic_vars`` hook run; every numeric entry of ``self.vars`` is an output
-    (``var_array``) and so is the net flow of every compartment (``flow_array``)."""
+    (``var_array``) and so is the net flow of every compartment (``flow_array``).  ``want_vars``
+    (a list of var labels) keeps only those outputs, in the reference's order: everything that
+    feeds none of them is eliminated from the device code."""
     from .basepop import BaseModel
 
     integer_state = method != 'explicit' and not diagnostics
@@ -706,9 +676,15 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
             for label, value in model.vars.items():
                 if isinstance(value, Sym) and value.is_bool:
                     continue
+                if want_vars is not None and label not in want_vars:
+                    continue
                 if isinstance(value, (Sym, numbers.Real)) and not isinstance(value, bool):
                     cm.diag_labels.append(label)
                     cm.diag_nodes.append(as_sym(value, 'vars[%r]' % label).n)
+            if want_vars is not None:
+                missing = [label for label in want_vars if label not in cm.diag_labels]
+                if missing:
+                    raise KeyError('the diagnostics pass defines no var(s) %s' % missing)
             cm.diag_flow_nodes = [as_sym(model.flows[label], 'flows[%r]' % label).n
                                   for label in cm.labels]
     finally:
@@ -725,7 +701,16 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
     cm.param_values = tr.param_values
     cm.param_is_int = tr.param_is_int
 
-    # ---- dead-code elimination + evaluation order --------------------------------------------
+    cm.order = live_order(cm)
+    cm.uses_time = any(g.nodes[n][0] == 'time' for n in cm.order)
+    return cm
+
+
+def live_order(cm):
+    """Dead-code elimination + evaluation order: the nodes reachable from the flow rates, the
+    checks and (diagnostics pass) the requested vars / net flows, in creation order, which is
+    topological."""
+    g = cm.graph
     roots = list(cm.flow_node) + list(cm.check_nodes) + list(cm.diag_nodes) + \
         list(cm.diag_flow_nodes)
     live = set()
@@ -738,9 +723,7 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
         node = g.nodes[n]
         if node[0] not in ('comp', 'param', 'time', 'su', 'const'):
             stack.extend(x for x in node[1:] if x >= 0)
-    cm.order = [n for n in range(len(g.nodes)) if n in live]   # creation order is topological
-    cm.uses_time = any(g.nodes[n][0] == 'time' for n in cm.order)
-    return cm
+    return [n for n in range(len(g.nodes)) if n in live]
 
 
 def _same(a, b):

@@ -66,6 +66,9 @@ typedef struct {
                                   their reduction and raises PD_ERR_COUNT_RANGE for a count that
                                   lands in the last (overflow) bin                               */
   int pad2;
+  long long pm_ld;             /* row stride (elements) of pm: M, or the chunk size when the host
+                                  staged this launch's member range on its own                   */
+  long long out_ld;            /* row stride of soln / final_state                               */
 } PdStochArgs;
 
 /* The tau-leap kernel keeps per-warp partial moment sums in shared memory and moves them to
@@ -96,6 +99,9 @@ typedef struct {
   const unsigned char *mask;   /* [M] or NULL: only members with mask[m] == mask_value run       */
   int n_time;
   int mask_value;
+  long long member0;           /* global id of member 0 of this launch (error reports)           */
+  long long pm_ld;             /* row stride (elements) of pm                                    */
+  long long out_ld;            /* row stride of soln / final_state                               */
 } PdExplicitArgs;
 
 typedef struct {
@@ -108,6 +114,9 @@ typedef struct {
   double *flow_soln;           /* [T][C][M] or NULL                                              */
   int n_time;
   int pad;
+  long long soln_ld;           /* row strides (elements) of soln, pm, and var_soln / flow_soln   */
+  long long pm_ld;
+  long long out_ld;
 } PdDiagArgs;
 
 #endif

@@ -27,17 +27,17 @@ pd_diag_kernel(const __grid_constant__ PdDiagLaunch L) {
   double pm[PD_NPM_DIM];
   pm[0] = 0.0;
 #pragma unroll
-  for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * M + m];
+  for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * a.pm_ld + m];
   for (int it = blockIdx.y; it < a.n_time; it += gridDim.y) {
     double y[PD_C], out[PD_NDIAG_DIM], flow[PD_C];
 #pragma unroll
-    for (int c = 0; c < PD_C; ++c) y[c] = a.soln[((size_t)it * PD_C + c) * M + m];
+    for (int c = 0; c < PD_C; ++c) y[c] = a.soln[((size_t)it * PD_C + c) * a.soln_ld + m];
     pd_diag(y, L.U, pm, a.times[it], a.su, out, flow);
 #pragma unroll
-    for (int v = 0; v < PD_NDIAG; ++v) a.var_soln[((size_t)it * PD_NDIAG + v) * M + m] = out[v];
+    for (int v = 0; v < PD_NDIAG; ++v) a.var_soln[((size_t)it * PD_NDIAG + v) * a.out_ld + m] = out[v];
     if (a.flow_soln) {
 #pragma unroll
-      for (int c = 0; c < PD_C; ++c) a.flow_soln[((size_t)it * PD_C + c) * M + m] = flow[c];
+      for (int c = 0; c < PD_C; ++c) a.flow_soln[((size_t)it * PD_C + c) * a.out_ld + m] = flow[c];
     }
   }
 }

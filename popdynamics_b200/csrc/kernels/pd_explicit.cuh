@@ -34,12 +34,12 @@ pd_explicit_kernel(const __grid_constant__ PdExplicitLaunch L) {
   double y[PD_C], f[PD_C], pm[PD_NPM_DIM];
   pm[0] = 0.0;
 #pragma unroll
-  for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * M + m];
+  for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * a.pm_ld + m];
 #pragma unroll
   for (int c = 0; c < PD_C; ++c) {
     y[c] = pd_load_y0(a.y0, a.y0_stride_c, a.y0_stride_m, c, m);
 #if PD_OUT_MODE == PD_OUT_FULL
-    a.soln[(size_t)c * M + m] = y[c];                       /* :671 */
+    a.soln[(size_t)c * a.out_ld + m] = y[c];                       /* :671 */
 #endif
   }
 
@@ -70,12 +70,12 @@ pd_explicit_kernel(const __grid_constant__ PdExplicitLaunch L) {
     }
 #if PD_OUT_MODE == PD_OUT_FULL
 #pragma unroll
-    for (int c = 0; c < PD_C; ++c) a.soln[((size_t)it * PD_C + c) * M + m] = y[c];  /* :688 */
+    for (int c = 0; c < PD_C; ++c) a.soln[((size_t)it * PD_C + c) * a.out_ld + m] = y[c];  /* :688 */
 #endif
   }
 #if PD_OUT_MODE == PD_OUT_FINAL
 #pragma unroll
-  for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * M + m] = y[c];
+  for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * a.out_ld + m] = y[c];
 #endif
-  if (!ok) pd_raise(a.err, PD_ERR_CHECKS, m, bad_at);
+  if (!ok) pd_raise(a.err, PD_ERR_CHECKS, a.member0 + m, bad_at);
 }

@@ -194,13 +194,13 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
   pm[0] = 0.0;
   if (active) {
 #pragma unroll
-    for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * M + m];
+    for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * a.pm_ld + m];
 #pragma unroll
     for (int c = 0; c < PD_C; ++c) {
       const double v = pd_load_y0(a.y0, a.y0_stride_c, a.y0_stride_m, c, m);
       y[c] = (pd_count)v;                                   /* :747-748 */
 #if PD_OUT_MODE == PD_OUT_FULL
-      a.soln[(size_t)c * M + m] = v;                        /* :755 */
+      a.soln[(size_t)c * a.out_ld + m] = v;                        /* :755 */
 #endif
     }
     rng.init(a, m);
@@ -239,7 +239,7 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
       if (active) {
 #pragma unroll
         for (int c = 0; c < PD_C; ++c)
-          a.soln[((size_t)flushed * PD_C + c) * M + m] = (double)ys[c];
+          a.soln[((size_t)flushed * PD_C + c) * a.out_ld + m] = (double)ys[c];
       }
 #elif PD_HIST_MOMENTS
       if (active) pd_hist_record(a, ys, flushed, a.member0 + m);
@@ -270,7 +270,7 @@ pd_gillespie_kernel(const __grid_constant__ PdGilLaunch L) {
   if (active) {
 #if PD_OUT_MODE == PD_OUT_FINAL
 #pragma unroll
-    for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * M + m] = (double)y[c];
+    for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * a.out_ld + m] = (double)y[c];
 #endif
     if (bad) pd_raise(a.err, bad, a.member0 + m, 0);
   }

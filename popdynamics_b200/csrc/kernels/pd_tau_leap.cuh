@@ -138,13 +138,13 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   pm[0] = 0.0;
   if (active) {
 #pragma unroll
-    for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * M + m];
+    for (int j = 0; j < PD_NPM; ++j) pm[j] = a.pm[(size_t)j * a.pm_ld + m];
 #pragma unroll
     for (int c = 0; c < PD_C; ++c) {
       const double v = pd_load_y0(a.y0, a.y0_stride_c, a.y0_stride_m, c, m);
       y[c] = (pd_count)v;                                   /* int() truncation, :805-806 */
 #if PD_OUT_MODE == PD_OUT_FULL
-      a.soln[(size_t)c * M + m] = v;                        /* row 0 = untruncated y, :813 */
+      a.soln[(size_t)c * a.out_ld + m] = v;                        /* row 0 = untruncated y, :813 */
 #endif
     }
     rng.init(a, m);
@@ -299,7 +299,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #if PD_OUT_MODE == PD_OUT_FULL
 #pragma unroll
       for (int c = 0; c < PD_C; ++c)
-        a.soln[((size_t)it * PD_C + c) * M + m] = (double)y[c];   /* :850-852 */
+        a.soln[((size_t)it * PD_C + c) * a.out_ld + m] = (double)y[c];   /* :850-852 */
 #endif
     }
 #if PD_OUT_MODE == PD_OUT_STATS
@@ -317,7 +317,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   if (active) {
 #if PD_OUT_MODE == PD_OUT_FINAL
 #pragma unroll
-    for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * M + m] = (double)y[c];
+    for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * a.out_ld + m] = (double)y[c];
 #endif
     if (!bad && rng.exhausted) bad = PD_ERR_STREAM;
     if (bad) pd_raise(a.err, bad, a.member0 + m, 0);

@@ -60,14 +60,39 @@ def allreduce_stats(result, group=None, device=None):
     return result
 
 
+def allgather_error(info, group=None, device=None):
+    """Make the device error flag of any rank known to every rank: returns the ``info`` triple
+    (err_code, err_member, err_where) of the failing member with the smallest global id, or
+    zeros.  Every rank must call it (it is a collective)."""
+    import torch
+    import torch.distributed as dist
+    mine = torch.tensor([int(info.get('err_code', 0)), int(info.get('err_member', -1)),
+                         int(info.get('err_where', 0))], dtype=torch.int64, device=device)
+    world = dist.get_world_size(group)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    failures = [tuple(int(v) for v in t.cpu()) for t in gathered if int(t[0]) != 0]
+    if not failures:
+        return dict(err_code=0, err_member=-1, err_where=0)
+    code, member, where = min(failures, key=lambda f: f[1])
+    return dict(err_code=code, err_member=member, err_where=where)
+
+
 def integrate_sharded(model_factory, method, n_members, rank=None, world_size=None, group=None,
-                      reduce_device=None, **kwargs):
+                      reduce_device=None, check=True, **kwargs):
     """Integrate this rank's shard of an ``n_members`` ensemble and all-reduce the statistics.
 
     ``model_factory(start, stop)`` builds the model for the global member range [start, stop)
-    (so that per-member parameter arrays are created for the shard only).  Keyword arguments go
-    to ``ensemble.integrate_ensemble``.  Returns ``(result, (start, stop))``; with
-    ``output='stats'`` the moments / histograms in ``result`` are the ensemble totals."""
+    (so that per-member parameter arrays are created for the shard only; it is also called for an
+    EMPTY range, ``start == stop``, when there are more ranks than members -- that rank launches
+    nothing but still joins the collectives).  Keyword arguments go to
+    ``ensemble.integrate_ensemble``.  Returns ``(result, (start, stop))``; with ``output='stats'``
+    the moments / histograms in ``result`` are the ensemble totals and ``result.n_total`` is the
+    global member count, so ``mean()`` / ``var()`` / ``quantiles()`` describe the whole ensemble.
+
+    Errors are collective too: the device error flag of every rank is gathered BEFORE the
+    statistics are reduced and, with ``check=True``, the reference's exception is raised on every
+    rank -- a failing shard can never leave the other ranks waiting in an all-reduce."""
     import torch.distributed as dist
     from . import ensemble
     if rank is None:
@@ -76,8 +101,20 @@ def integrate_sharded(model_factory, method, n_members, rank=None, world_size=No
         world_size = dist.get_world_size(group) if dist.is_initialized() else 1
     start, stop = shard_range(n_members, rank, world_size)
     model = model_factory(start, stop)
-    result = ensemble.integrate_ensemble(model, method, n_members=stop - start,
-                                         member_offset=start, **kwargs)
-    if kwargs.get('output') == 'stats' and world_size > 1:
-        allreduce_stats(result, group=group, device=reduce_device)
+    if stop > start:
+        result = ensemble.integrate_ensemble(model, method, n_members=stop - start,
+                                             member_offset=start, check=False, **kwargs)
+    else:
+        result = ensemble.empty_result(model, method, member_offset=start, **kwargs)
+    info = dict(result.info)
+    if world_size > 1 and dist.is_initialized():
+        info = allgather_error(info, group=group, device=reduce_device)
+        result.info.update(info)
+        if kwargs.get('output') == 'stats' and not info['err_code']:
+            allreduce_stats(result, group=group, device=reduce_device)
+            if getattr(result, 'moments_from', None) == 'hist':
+                result.derive_moments()
+    result.n_total = int(n_members)
+    if check:
+        ensemble.raise_device_error(info, method)
     return result, (start, stop)

@@ -88,6 +88,22 @@ def _member_param_block(cm, n_member, like=None):
     return block
 
 
+def _member_param_rows(cm, n_member):
+    """The swept parameter columns as the model holds them (no [P][M] copy): list of [M] float64
+    arrays in slot order, or None."""
+    slots = cm.member_param_slots()
+    if not slots:
+        return None
+    rows = []
+    for k in slots:
+        values = cm.param_values[k]
+        if values.size != n_member:
+            raise ValueError('parameter %r has %d entries for %d members'
+                             % (cm.param_labels[k], values.size, n_member))
+        rows.append(values)
+    return rows
+
+
 def _initial_state(model, y, n_member):
     """[C] shared or [C][M] per-member initial compartments."""
     per_member = any(isinstance(v, numpy.ndarray) for v in y)
@@ -107,7 +123,8 @@ class EnsembleResult(object):
         self.output = None
         self.labels = []
         self.times = None
-        self.n_members = 0
+        self.n_members = 0        # members integrated by THIS launch (the shard)
+        self.n_total = None       # members behind the statistics once shards have been reduced
         self.member_offset = 0
         self.seed = None
         self.soln = None          # [T][C][M]
@@ -128,11 +145,11 @@ class EnsembleResult(object):
         return m.astype(numpy.float64) if m.dtype != numpy.float64 else m
 
     def mean(self, n_total=None):
-        n = float(n_total or self.n_members)
+        n = float(n_total or self.n_total or self.n_members)
         return self._moments_host()[..., 0] / n
 
     def var(self, n_total=None, ddof=0):
-        n = float(n_total or self.n_members)
+        n = float(n_total or self.n_total or self.n_members)
         m = self._moments_host()
         mean = m[..., 0] / n
         return (m[..., 1] / n - mean * mean) * (n / (n - ddof))
@@ -223,10 +240,22 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
         y0, y0_per_member = _initial_state(model, y, M)
     else:
         y0_per_member = 1 if (y0.ndim == 2) else 0
+    param_rows = None
+    if method != 'explicit' and count_bits == 32:
+        # 32-bit counts: an initial state at or above 2**31 would be silently saturated by the
+        # double -> int conversion on the device; numpy / Python ints never wrap
+        peak = float(y0.max()) if (y0.numel() if _is_torch(y0) else y0.size) else 0.0
+        if not peak < 2.0 ** 31:
+            raise ValueError('initial compartment %.17g does not fit count_bits=32; use '
+                             'count_bits=64' % peak)
     if member_params is None:
-        member_params = _member_param_block(cm, M)
+        # the swept columns go to the library as they are: one pointer per parameter, staged
+        # chunk by chunk inside the run (no [P][M] host copy)
+        rows = _member_param_rows(cm, M)
+        if rows is not None:
+            param_rows = capi.row_pointers(rows)
     uniform = cm.uniform_params()
-    keep = [tt, y0, member_params, uniform]
+    keep = [tt, y0, member_params, uniform, param_rows]
 
     def alloc(shape, dtype):
         return numpy.empty(shape, dtype=dtype)
@@ -241,6 +270,7 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
         run.y0, run.y0_per_member, run.n_time = capi.address(y0), y0_per_member, T
         run.uniform_params = capi.address(uniform)
         run.member_params = capi.address(member_params)
+        run.member_param_rows = param_rows[1] if param_rows else None
         n_sub_arg = n_sub if len(n_sub) else numpy.zeros(1, dtype=numpy.int32)
         keep.append(n_sub_arg)
         run.n_sub, run.dt = capi.address(n_sub_arg), capi.address(dt) if len(dt) else None
@@ -256,6 +286,7 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
         run.y0, run.y0_per_member, run.n_time = capi.address(y0), y0_per_member, T
         run.uniform_params = capi.address(uniform)
         run.member_params = capi.address(member_params)
+        run.member_param_rows = param_rows[1] if param_rows else None
         run.target_times = capi.address(tt)
         run.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         if uniforms is not None:
@@ -328,6 +359,39 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
     if res.moments_from == 'hist' and not result.err_code:
         res.derive_moments()
     del keep
+    return res
+
+
+def empty_result(model, method, output='full', member_offset=0, hist_bins=0, hist_max=None,
+                 hist_times=None, statistics='host', device=None, seed=0,
+                 moments_from='kernel', **_ignored):
+    """The result of a launch over ZERO members (a rank whose shard is empty): zeroed statistics
+    of the right shape, so that the rank can still join the all-reduce; no kernel runs."""
+    device = model.device if device is None else device
+    res = EnsembleResult()
+    res.method, res.output, res.labels = method, output, list(model.labels)
+    res.times = numpy.asarray([float(t) for t in model.target_times])
+    res.member_offset, res.seed, res.device = member_offset, seed, device
+    res.info = dict(err_code=0, err_member=-1, err_where=0, kernel_ms=0.0, n_steps=0,
+                    h2d_bytes=0, d2h_bytes=0)
+    C, T = len(model.labels), len(model.target_times)
+    res.moments_from = moments_from if output == 'stats' else None
+    if output == 'stats':
+        def zeros(shape, np_dtype, torch_dtype):
+            if statistics == 'device':
+                import torch
+                return torch.zeros(shape, dtype=getattr(torch, torch_dtype),
+                                   device=torch.device('cuda', device))
+            return numpy.zeros(shape, np_dtype)
+        res.moments = zeros((T, C, 2), numpy.uint64, 'int64')
+        if hist_bins:
+            row, shift, rows = _hist_setup(T, C, hist_bins, hist_max, hist_times)
+            res.hist = zeros((len(rows), C, hist_bins), numpy.uint32, 'int32')
+            res.hist_times, res.hist_shift, res.hist_bins = rows, shift, hist_bins
+    elif output == 'final':
+        res.final = numpy.zeros((C, 0))
+    else:
+        res.soln = numpy.zeros((T, C, 0))
     return res
 
 
@@ -429,6 +493,8 @@ def integrate_ensemble(model, method='explicit', n_members=None, output='full', 
                        hist_max=hist_max, hist_times=hist_times, min_blocks=min_blocks,
                        statistics=statistics, moments_from=moments_from, **buffers)
     res.member_offset, res.segment = member_offset, segment
+    if method == 'explicit' and res.info.get('err_code'):
+        res.info['err_member'] += int(member_offset)     # the explicit kernel counts from 0
     if check:
         raise_device_error(res.info, method)
     return res
@@ -534,7 +600,8 @@ class DiagnosticsResult(object):
         return soln[..., c, :] / self.var('population')
 
 
-def diagnostics(model, result, method=None, want_flows=False, device=None, block=256):
+def diagnostics(model, result, method=None, want_flows=False, device=None, block=256,
+                want_vars=None, out=None):
     """The diagnostics pass (``calculate_diagnostics``, /root/reference/basepop.py:911-960) for
     every member of an ensemble result: ``calculate_vars`` / ``calculate_flows`` /
     ``calculate_diagnostic_vars`` traced once and evaluated on the device at every stored time
@@ -543,11 +610,15 @@ def diagnostics(model, result, method=None, want_flows=False, device=None, block
 
     Scale-up vars: for the explicit integrator the reference never re-evaluates them in this pass,
     they keep the value of the last derivative call -- reproduced here; a hook
-    that calls ``calculate_scaleup_vars()`` itself gets them at the stored time."""
+    that calls ``calculate_scaleup_vars()`` itself gets them at the stored time.
+
+    ``want_vars=['proportion']`` evaluates and stores only the named vars (BASELINE config 5 reads
+    one scalar per member, /root/reference/examples/rmit_tb_model.py:143): 8 bytes per member and
+    time leave the device instead of 8 V.  ``out`` supplies the [T][V][M] (or [V][M]) buffer."""
     method = method or result.method
     device = result.device if device is None else device
     model.check_flow_transfers()
-    cm = compiler.compile_model(model, method, diagnostics=True)
+    cm = compiler.compile_model(model, method, diagnostics=True, want_vars=want_vars)
     if not cm.diag_nodes:
         raise ValueError('the model defines no vars')
     soln = result.soln if result.soln is not None else result.final
@@ -567,7 +638,7 @@ def diagnostics(model, result, method=None, want_flows=False, device=None, block
                             cm.n_param, len(cm.member_param_slots()), cm.n_su, cm.n_flow,
                             block=block)
         _KERNEL_CACHE[key] = kernel
-    out = DiagnosticsResult()
+    out_buffer, out = out, DiagnosticsResult()
     out.var_labels, out.labels, out.times = list(cm.diag_labels), list(cm.labels), times
 
     def like(shape):
@@ -576,13 +647,18 @@ def diagnostics(model, result, method=None, want_flows=False, device=None, block
             return torch.empty(shape, dtype=torch.float64, device=soln.device)
         return numpy.empty(shape, dtype=numpy.float64)
 
-    out.vars = like((T, V, M))
+    if out_buffer is not None:
+        out.vars = out_buffer.reshape((T, V, M))
+    else:
+        out.vars = like((T, V, M))
     out.flows = like((T, C, M)) if want_flows else None
     run = capi.DiagRun()
     run.n_member, run.n_time, run.n_var = M, T, V
     run.soln = capi.address(soln)
     uniform = cm.uniform_params()
-    member_params = _member_param_block(cm, M)
+    member_params = None
+    rows = _member_param_rows(cm, M)
+    param_rows = capi.row_pointers(rows) if rows is not None else None
     su_row = None
     if cm.n_su:
         t_last = result.info.get('last_eval_time')
@@ -590,9 +666,10 @@ def diagnostics(model, result, method=None, want_flows=False, device=None, block
             raise ValueError('the result does not record the time of the last derivative call')
         su_row = numpy.array([model.scaleup_fns[label](t_last) for label in cm.su_labels],
                              dtype=numpy.float64)
-    keep = [uniform, member_params, su_row, times]
+    keep = [uniform, member_params, su_row, times, param_rows]
     run.uniform_params = capi.address(uniform)
     run.member_params = capi.address(member_params)
+    run.member_param_rows = param_rows[1] if param_rows else None
     run.times = capi.address(times)
     run.scaleup_row = capi.address(su_row)
     run.var_soln = capi.address(out.vars)

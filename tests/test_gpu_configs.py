@@ -1,0 +1,254 @@
+"""GPU tests of the BASELINE.json configurations as bench.py runs them (examples/configs.py): the
+same builders at sizes the oracle finishes in seconds, members embedded in the sweeps compared
+with the reference's golden vectors and with the oracle, the chunked host-staging pipeline of the
+C-ABI against a single resident launch, and the multi-rank path over NCCL when the box has two
+GPUs.  Bit-exact everywhere (explicit fp64, integer counts)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from examples import configs
+from oracle import oracle
+from popdynamics_b200 import compiler, distributed, ensemble
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_explicit_member(model, i):
+    """Oracle run of member i of a sweep model (explicit)."""
+    model.check_flow_transfers()
+    cm = compiler.compile_model(model, 'explicit')
+    om = oracle.OracleModel(cm)
+    soln, _, err = om.explicit(model.get_init_list(), model.target_times,
+                               params=om.member_params(i))
+    assert err == 0
+    return soln
+
+
+# ------------------------------------------------------------------------------- config 2
+def test_config2_seir_sweep_50_years_golden_member_and_oracle_members(golden):
+    n = 4096
+    model = configs.seir_sweep(0, n)
+    res = model.integrate_ensemble('explicit', n_members=n, output='final')
+    # member 0 = the measles base case: 18 250 days, 376 696 derivative evaluations
+    assert np.array_equal(res.final[:, 0], golden[configs.SEIR_GOLDEN_KEY])
+    assert res.info['n_steps'] == 376696 * n
+    for i in (1, 77, n - 1):
+        assert np.array_equal(res.final[:, i], _oracle_explicit_member(model, i)[-1]), i
+
+
+def test_config2_trajectory_rows_of_the_golden_member(golden):
+    model = configs.seir_sweep(0, 64)
+    res = model.integrate_ensemble('explicit', n_members=64, output='full')
+    assert np.array_equal(res.soln[::365, :, 0], golden['seird_explicit_18250_every365'])
+
+
+def test_sweeps_do_not_depend_on_the_shard_they_are_built_for():
+    whole = configs.rmit_sweep(0, 3 * configs.BLOCK + 17)
+    part = configs.rmit_sweep(configs.BLOCK - 5, 2 * configs.BLOCK + 9)
+    for key in ('beta', 'rho', 'sigma1', 'sigma2', 'sigma3'):
+        assert np.array_equal(whole.params[key][configs.BLOCK - 5:2 * configs.BLOCK + 9],
+                              part.params[key])
+
+
+# ------------------------------------------------------------------------------- config 5
+def test_config5_rmit_sweep_golden_points_and_chunked_staging(golden, monkeypatch):
+    n = 20000
+    model = configs.rmit_sweep(0, n)
+    # one resident launch ...
+    whole = model.integrate_ensemble('explicit', n_members=n, output='final')
+    assert whole.info['n_launch'] == 1
+    # ... against the chunk pipeline (host parameter columns staged 3000 members at a time,
+    # ragged last chunk), final state kept on the device
+    monkeypatch.setenv('POPDYN_CHUNK_MEMBERS', '3000')
+    out = torch.empty((6, n), dtype=torch.float64, device='cuda')
+    chunked = model.integrate_ensemble('explicit', n_members=n, output='final', out=out)
+    assert chunked.info['n_launch'] == 7
+    assert np.array_equal(out.cpu().numpy(), whole.final)
+    # host output through the pipeline as well
+    host = model.integrate_ensemble('explicit', n_members=n, output='final')
+    assert host.info['n_launch'] == 7 and np.array_equal(host.final, whole.final)
+    monkeypatch.delenv('POPDYN_CHUNK_MEMBERS')
+    # vars['proportion'] of the final state, one scalar per member (rmit_tb_model.py:143)
+    prop = np.empty((1, n))
+    d = ensemble.diagnostics(model, chunked, want_vars=['proportion'], out=prop)
+    assert d.var_labels == ['proportion'] and d.vars.shape == (1, n)
+    assert np.array_equal(prop[0, :6], golden['rmit_fig2_proportion'])
+    assert np.array_equal(whole.final[:, :6].T, golden['rmit_fig2_final'])
+    every = ensemble.diagnostics(model, whole)
+    assert np.array_equal(every.var('proportion'), prop[0])
+    for i in (6, 4321, n - 1):
+        assert np.array_equal(whole.final[:, i], _oracle_explicit_member(model, i)[-1]), i
+
+
+def test_chunked_pipeline_full_trajectories_and_stochastic_outputs(monkeypatch):
+    # FULL output (rows = T*C) and a stochastic run with swept parameters through the chunks
+    n = 5000
+    model = configs.seir_sweep(0, n)
+    model.make_times(0, 30, 1)
+    whole = model.integrate_ensemble('explicit', n_members=n, output='full')
+    monkeypatch.setenv('POPDYN_CHUNK_MEMBERS', '1024')
+    parts = model.integrate_ensemble('explicit', n_members=n, output='full')
+    assert parts.info['n_launch'] == 5 and np.array_equal(parts.soln, whole.soln)
+    monkeypatch.delenv('POPDYN_CHUNK_MEMBERS')
+    rng = np.random.default_rng(3)
+    strains = helpers.make_model('strains', params=[('rate_recover', rng.uniform(5e-3, 2e-2, n))])
+    strains.make_times(0, 40, 1)
+    a = strains.integrate_ensemble('discrete_time_stochastic', n_members=n, output='final',
+                                   seed=4, member_offset=100)
+    monkeypatch.setenv('POPDYN_CHUNK_MEMBERS', '1536')
+    b = strains.integrate_ensemble('discrete_time_stochastic', n_members=n, output='final',
+                                   seed=4, member_offset=100)
+    assert b.info['n_launch'] == 4 and np.array_equal(a.final, b.final)
+    s = strains.integrate_ensemble('discrete_time_stochastic', n_members=n, output='stats',
+                                   seed=4, member_offset=100, hist_bins=4096, hist_max=4095)
+    monkeypatch.delenv('POPDYN_CHUNK_MEMBERS')
+    t = strains.integrate_ensemble('discrete_time_stochastic', n_members=n, output='stats',
+                                   seed=4, member_offset=100, hist_bins=4096, hist_max=4095)
+    assert s.info['n_launch'] == 4 and t.info['n_launch'] == 1
+    assert np.array_equal(s.moments, t.moments) and np.array_equal(s.hist, t.hist)
+    assert int(s.info['n_steps']) == int(t.info['n_steps']) == 40 * n
+
+
+def test_error_member_is_global_across_chunks(monkeypatch):
+    # checks() failing in a later chunk reports the GLOBAL member id
+    n = 4000
+    beta = np.full(n, 50.)
+    beta[3333] = 5e5                         # explicit Euler blows up for this member
+    p = dict(helpers.RMIT, beta=beta)
+    from examples import models
+    model = models.RmitTbModel(p)
+    model.make_times(0, 50., 1.)
+    monkeypatch.setenv('POPDYN_CHUNK_MEMBERS', '1000')
+    res = model.integrate_ensemble('explicit', n_members=n, output='final', check=False)
+    assert res.info['n_launch'] == 4 and res.info['err_code'] == 1
+    assert res.info['err_member'] == 3333
+
+
+# ------------------------------------------------------------------------------- config 4
+def test_config4_tb_gillespie_members_equal_the_oracle():
+    model = configs.tb_gillespie()
+    model.make_times(1950, 1953, 1.)
+    method = 'continuous_time_stochastic'
+    n, seed, offset = 96, 0, 12345
+    res = model.integrate_ensemble(method, n_members=n, output='full', seed=seed,
+                                   member_offset=offset, count_bits=32)
+    cm = helpers.compiled(model, method)
+    om = oracle.OracleModel(cm)
+    for i in (0, 31, 95):
+        want, n_event, err = om.gillespie(model.get_init_list(), model.target_times,
+                                          oracle.Rng('philox', seed=seed, member=offset + i))
+        assert err == 0 and np.array_equal(res.soln[:, :, i], want), i
+    final = model.integrate_ensemble(method, n_members=n, output='final', seed=seed,
+                                     member_offset=offset, count_bits=64)
+    assert np.array_equal(final.final, res.soln[-1])
+
+
+def test_initial_state_beyond_32_bit_counts_is_rejected():
+    model = helpers.make_model('strains')
+    model.make_times(0, 5, 1)
+    model.set_compartment('susceptible', 3e9)
+    with pytest.raises(ValueError, match='count_bits=32'):
+        model.integrate_ensemble('discrete_time_stochastic', n_members=64, output='final',
+                                 count_bits=32)
+    res = model.integrate_ensemble('discrete_time_stochastic', n_members=64, output='final',
+                                   count_bits=64)
+    assert res.final[0].min() > 2.9e9
+
+
+# ------------------------------------------------------------------------------- config 5b
+def test_config5b_hybrid_switching_over_50_days_matches_the_oracle_loop():
+    n, seed = 2048, 5
+    model = configs.mix_model()
+    res = ensemble.integrate_hybrid(model, configs.MIX_SEGMENTS, n, configs.MIX_CUTOFF, seed=seed,
+                                    member_offset=7 * n, output='final')
+    final = res.final.cpu().numpy()
+    modes = res.modes.cpu().numpy()
+    assert 0 < modes[1:].sum() < modes[1:].size
+    for i in (0, 999, n - 1):
+        rows, want_modes = helpers.oracle_hybrid(
+            configs.mix_model, configs.MIX_SEGMENTS, configs.MIX_CUTOFF,
+            lambda k: oracle.Rng('philox', seed=seed, member=(k << 40) + 7 * n + i))
+        assert [int(v) for v in modes[:, i]] == [int(w == 'explicit') for w in want_modes]
+        assert np.array_equal(final[:, i], rows[-1]), i
+
+
+# ------------------------------------------------------------------------------- multi-GPU
+def _nccl_worker(rank, world, port, queue):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        def factory(start, stop):
+            m = configs.strains()
+            m.make_times(0, 60, 1)
+            m.device = rank
+            return m
+        res, (start, stop) = distributed.integrate_sharded(
+            factory, 'discrete_time_stochastic', 20001, reduce_device=dev, output='stats',
+            seed=9, hist_bins=2048, hist_max=2047, statistics='device', moments_from='hist',
+            count_bits=32)
+        q = res.quantiles([0.25, 0.5, 0.975]).cpu().numpy()
+        if rank == 0:
+            queue.put((res.moments.cpu().numpy(), res.hist.cpu().numpy(), q, res.mean(),
+                       res.n_total, (start, stop)))
+        # a sweep whose failing member lives on the LAST rank: every rank must raise
+        def bad_factory(start, stop):
+            from examples import models
+            beta = np.full(stop - start, 50.)
+            if start <= 3999 < stop:
+                beta[3999 - start] = 5e5
+            m = models.RmitTbModel(dict(helpers.RMIT, beta=beta))
+            m.make_times(0, 50., 1.)
+            m.device = rank
+            return m
+        try:
+            distributed.integrate_sharded(bad_factory, 'explicit', 4000, reduce_device=dev,
+                                          output='final')
+            raised = None
+        except AssertionError as exc:
+            raised = str(exc)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, raised)
+        if rank == 0:
+            queue.put(gathered)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpus_over_nccl_equal_one_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (run with gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    moments, hist, q, mean, n_total, shard = queue.get(timeout=300)
+    raised = queue.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert n_total == 20001 and shard == (0, 10001)
+    m = configs.strains()
+    m.make_times(0, 60, 1)
+    one = m.integrate_ensemble('discrete_time_stochastic', n_members=20001, output='stats',
+                               seed=9, hist_bins=2048, hist_max=2047, moments_from='hist',
+                               count_bits=32)
+    assert np.array_equal(hist, one.hist.view(np.int32))
+    assert np.array_equal(moments, one.moments.view(np.int64))
+    assert np.array_equal(q, one.quantiles([0.25, 0.5, 0.975]))
+    assert np.array_equal(mean, one.mean())
+    assert all(r is not None and 'member 3999' in r for r in raised), raised
