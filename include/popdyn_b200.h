@@ -123,7 +123,8 @@ typedef struct {
   const double *const *member_param_rows; /* [n_member_param] HOST array of row pointers, each to
                                      [M] doubles (host or device): the swept parameter columns as
                                      the caller holds them, instead of one [P][M] block; used when
-                                     member_params is NULL                                      */
+                                     member_params is NULL.  A NULL row is a column the compiled
+                                     kernel never reads: nothing is staged for it               */
 } pd_stoch_run;
 
 typedef struct {

@@ -8,7 +8,7 @@ Python loops can be timed on the GPU box, where ``/root/reference`` does not exi
 TEST / BASELINE INFRASTRUCTURE ONLY.  Nothing is copied: ``basepop.py`` is byte-compiled where it
 lies (``py_compile``), and of every example script only the model ``class`` definitions are
 compiled (the scripts run their main routine and import pylab at import time, so they cannot be
-imported as modules -- same AST extraction as oracle/reference.py).  Outputs are ``.pyc`` files
+imported as modules -- same AST extraction as oracle/reference.py).  Outputs are ``.pycode`` (CPython bytecode) files
 under ``oracle/_ref/`` only; the directory is git-ignored and travels to the box with the built
 ``.so`` files.  The one third-party name the reference needs, ``past.utils.old_div`` (package
 ``future``, not installed), is restated in oracle/ref_shim/.
@@ -32,7 +32,7 @@ def build():
     if not os.path.isfile(source):
         return False
     os.makedirs(OUT, exist_ok=True)
-    py_compile.compile(source, cfile=os.path.join(OUT, 'basepop.pyc'), dfile='basepop.py',
+    py_compile.compile(source, cfile=os.path.join(OUT, 'basepop.pycode'), dfile='basepop.py',
                        doraise=True)
     for script in EXAMPLES:
         path = os.path.join(REFERENCE_DIR, 'examples', script)
@@ -41,7 +41,7 @@ def build():
         classes = [node for node in tree.body if isinstance(node, ast.ClassDef)]
         code = compile(ast.Module(body=classes, type_ignores=[]), 'examples/' + script, 'exec')
         data = importlib._bootstrap_external._code_to_timestamp_pyc(code)
-        with open(os.path.join(OUT, 'classes_' + script[:-3] + '.pyc'), 'wb') as handle:
+        with open(os.path.join(OUT, 'classes_' + script[:-3] + '.pycode'), 'wb') as handle:
             handle.write(data)
     with open(os.path.join(OUT, 'BUILT_FROM'), 'w') as handle:
         handle.write('%s (python %s)\n' % (REFERENCE_DIR, sys.version.split()[0]))

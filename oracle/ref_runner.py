@@ -28,7 +28,7 @@ _modules = {}
 
 
 def available():
-    return os.path.isfile(os.path.join(REF, 'basepop.pyc'))
+    return os.path.isfile(os.path.join(REF, 'basepop.pycode'))
 
 
 def basepop():
@@ -38,7 +38,7 @@ def basepop():
         if shim not in sys.path:
             sys.path.insert(0, shim)
         loader = importlib.machinery.SourcelessFileLoader('reference_basepop_compiled',
-                                                          os.path.join(REF, 'basepop.pyc'))
+                                                          os.path.join(REF, 'basepop.pycode'))
         spec = importlib.util.spec_from_loader(loader.name, loader)
         module = importlib.util.module_from_spec(spec)
         loader.exec_module(module)
@@ -51,7 +51,7 @@ def example_classes(script):
     import numpy
     module = basepop()
     from past.utils import old_div
-    with open(os.path.join(REF, 'classes_' + script + '.pyc'), 'rb') as handle:
+    with open(os.path.join(REF, 'classes_' + script + '.pycode'), 'rb') as handle:
         code = marshal.loads(handle.read()[16:])
     namespace = {'basepop': module, 'old_div': old_div, 'math': math, 'numpy': numpy,
                  'range': range, 'map': map, '__name__': 'reference_example'}

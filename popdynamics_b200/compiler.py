@@ -706,6 +706,23 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
     return cm
 
 
+def params_read_by(cm, roots):
+    """Parameter slots the expression graph reads on the way to ``roots`` (node ids)."""
+    g = cm.graph
+    seen, slots, stack = set(), set(), list(roots)
+    while stack:
+        n = stack.pop()
+        if n in seen:
+            continue
+        seen.add(n)
+        node = g.nodes[n]
+        if node[0] == 'param':
+            slots.add(node[1])
+        elif node[0] not in ('comp', 'time', 'su', 'const'):
+            stack.extend(x for x in node[1:] if x >= 0)
+    return slots
+
+
 def live_order(cm):
     """Dead-code elimination + evaluation order: the nodes reachable from the flow rates, the
     checks and (diagnostics pass) the requested vars / net flows, in creation order, which is

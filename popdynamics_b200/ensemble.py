@@ -658,6 +658,12 @@ def diagnostics(model, result, method=None, want_flows=False, device=None, block
     uniform = cm.uniform_params()
     member_params = None
     rows = _member_param_rows(cm, M)
+    if rows is not None:
+        # only the swept columns the requested outputs read are staged (config 5's `proportion`
+        # reads none: 8 bytes per member leave the device and nothing but the state goes in)
+        used = compiler.params_read_by(cm, list(cm.diag_nodes) +
+                                       (list(cm.diag_flow_nodes) if want_flows else []))
+        rows = [r if k in used else None for k, r in zip(cm.member_param_slots(), rows)]
     param_rows = capi.row_pointers(rows) if rows is not None else None
     su_row = None
     if cm.n_su:

@@ -118,12 +118,18 @@ def test_chunked_pipeline_full_trajectories_and_stochastic_outputs(monkeypatch):
 def test_error_member_is_global_across_chunks(monkeypatch):
     # checks() failing in a later chunk reports the GLOBAL member id
     n = 4000
-    beta = np.full(n, 50.)
-    beta[3333] = 5e5                         # explicit Euler blows up for this member
-    p = dict(helpers.RMIT, beta=beta)
+    # explicit Euler at dt = .05 diverges to NaN for these RMIT parameters (see
+    # test_default_checks_report_the_reference_failure_index); every other member is benign
+    bad = dict(rho=0.4675096681435942, sigma1=0.4864215594357471, sigma2=0.40346161064467484,
+               sigma3=0.40408850758699627, beta=462.931574029995)
+    p = dict(helpers.RMIT)
+    for key, value in bad.items():
+        column = np.full(n, 50. if key == 'beta' else helpers.RMIT.get(key, 0.))
+        column[3333] = value
+        p[key] = column
     from examples import models
     model = models.RmitTbModel(p)
-    model.make_times(0, 50., 1.)
+    model.make_times(0, 500., 1.)
     monkeypatch.setenv('POPDYN_CHUNK_MEMBERS', '1000')
     res = model.integrate_ensemble('explicit', n_members=n, output='final', check=False)
     assert res.info['n_launch'] == 4 and res.info['err_code'] == 1
@@ -158,7 +164,7 @@ def test_initial_state_beyond_32_bit_counts_is_rejected():
                                  count_bits=32)
     res = model.integrate_ensemble('discrete_time_stochastic', n_members=64, output='final',
                                    count_bits=64)
-    assert res.final[0].min() > 2.9e9
+    assert res.final.sum(axis=0).min() > 2.9e9      # the epidemic moves them, nothing saturates
 
 
 # ------------------------------------------------------------------------------- config 5b
@@ -202,11 +208,17 @@ def _nccl_worker(rank, world, port, queue):
         # a sweep whose failing member lives on the LAST rank: every rank must raise
         def bad_factory(start, stop):
             from examples import models
-            beta = np.full(stop - start, 50.)
-            if start <= 3999 < stop:
-                beta[3999 - start] = 5e5
-            m = models.RmitTbModel(dict(helpers.RMIT, beta=beta))
-            m.make_times(0, 50., 1.)
+            bad = dict(rho=0.4675096681435942, sigma1=0.4864215594357471,
+                       sigma2=0.40346161064467484, sigma3=0.40408850758699627,
+                       beta=462.931574029995)
+            p = dict(helpers.RMIT)
+            for key, value in bad.items():
+                column = np.full(stop - start, 50. if key == 'beta' else helpers.RMIT.get(key, 0.))
+                if start <= 3999 < stop:
+                    column[3999 - start] = value
+                p[key] = column
+            m = models.RmitTbModel(p)
+            m.make_times(0, 500., 1.)
             m.device = rank
             return m
         try:
