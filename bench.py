@@ -836,48 +836,65 @@ def config_hybrid(g, args):
 
 
 def config_adaptive(g, args):
-    """Config 6: the adaptive solver behind integrate('scipy') on the SEIR-demography sweep."""
+    """Config 6: the adaptive solver behind integrate('scipy') on the SEIR-demography sweep.
+    The reference itself cannot run this model through odeint beyond a few hundred days (LSODA
+    evaluates the derivative on a slightly negative state and the reference's checks() assert
+    fires), so the parity spot-check is a separate 300-day run against the odeint golden."""
     from examples import configs
     from popdynamics_b200 import capi, distributed
-    if 'scipy' not in capi.METHOD_CODES:
-        return None
+    torch = g.torch
     total = args.adaptive_members
     s0, s1 = distributed.shard_range(total, g.rank, g.world)
+    M = s1 - s0
+    short = configs.seir_sweep(s0, min(s1, s0 + 4096))
+    short.device = g.local_rank
+    short.make_times(0, 300, 1)
+    chk = short.integrate_ensemble('scipy', n_members=min(M, 4096), output='full',
+                                   device=g.local_rank)
     model = configs.seir_sweep(s0, s1)
     model.device = g.local_rank
-    model.integrate_ensemble('scipy', n_members=min(4096, s1 - s0), output='final',
-                             device=g.local_rank) if s1 - s0 > 4096 else None
     g.barrier()
     t0 = time.perf_counter()
-    res = model.integrate_ensemble('scipy', n_members=s1 - s0, output='final',
-                                   device=g.local_rank)
+    res = model.integrate_ensemble('scipy', n_members=M, output='final', device=g.local_rank,
+                                   check=False)
     g.barrier()
     wall = g.max_over_ranks(time.perf_counter() - t0)
     ms = g.max_over_ranks(res.info['kernel_ms'])
     steps = g.sum_over_ranks(res.info['n_steps'])
-    g.launches += res.info['n_launch']
+    g.launches += res.info['n_launch'] + 1
     if g.rank != 0:
         return None
-    gold = golden()
-    parity = None
-    if 'seird_odeint_18250_final' in gold.files:
-        got = np.asarray(res.final)[:, 0]
-        want = gold['seird_odeint_18250_final']
-        rel = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)))
-        parity = {'what': 'member 0 vs the unmodified reference\'s integrate(\'scipy\') '
-                          '(scipy odeint, LSODA) final state: max relative difference %.2e '
-                          '(tolerance 1e-5, DESIGN.md)' % rel, 'ok': rel < 1e-5}
+    want = golden()['seird_odeint_300']
+    got = np.asarray(chk.soln)[:, :, 0]
+    rel = float(np.abs(got - want).max() / np.abs(want).max())
+    fp64_peak = capi.microbench(0, g.local_rank)
+    # 7 derivative evaluations of 39 fp64 operations + ~28 C stage / error operations per step
+    ops = 7 * EXPLICIT_OPS['seir'] + 28 * 4 + 60
+    achieved = ops * (res.info['n_steps'] / (res.info['kernel_ms'] * 1e-3)) / 1e9
     return {
-        'config': '6: SEIR-demography sweep through the adaptive Dormand-Prince 5(4) solver '
-                  '(integrate(\'scipy\') equivalent), make_times(0, 18250, 1)',
-        'n_gpus': g.world, 'scaling': 'strong', 'members_total': total,
-        'ms': ms, 'value': steps / (ms * 1e-3), 'unit': 'accepted+rejected steps/s',
+        'config': '6: SEIR-demography sweep through the adaptive Dormand-Prince 5(4) integrator '
+                  '(integrate(\'scipy\') equivalent, rtol = atol = 1.49e-8), '
+                  'make_times(0, 18250, 1)',
+        'n_gpus': g.world, 'scaling': 'strong', 'members_total': total, 'members_per_gpu': M,
+        'ms': ms, 'value': steps / (ms * 1e-3), 'unit': 'attempted steps/s',
         'steps_per_member': steps / total, 'members_per_sec': total / (ms * 1e-3),
         'dtype': 'f64', 'data': 'synthetic',
-        'e2e': {'value': steps / wall, 'unit': 'steps/s',
+        'e2e': {'value': steps / wall, 'unit': 'attempted steps/s',
                 'h2d_bytes_per_step': int(res.info['h2d_bytes']),
                 'd2h_bytes_per_step': int(res.info['d2h_bytes']), 'seconds': wall},
-        'roofline': None, 'parity': parity,
+        'roofline': {'bound': 'fp64 pipe', 'kernel': 'pd_adaptive_kernel', 'achieved': achieved,
+                     'peak': fp64_peak, 'unit': 'G fp64 op/s', 'frac': achieved / fp64_peak,
+                     'traffic': None,
+                     'per_unit': '%.0f fp64 operations per attempted step (7 derivative '
+                                 'evaluations + stage combinations + error norm)' % ops},
+        'cpu_baseline': None,
+        'parity': {'what': 'member 0 over 300 days vs the unmodified reference\'s '
+                           'integrate(\'scipy\') (odeint / LSODA) trajectory: max difference '
+                           '%.2e of the largest compartment (tolerance 2e-6, DESIGN.md); members '
+                           'flagged by checks() in the 50-year run: %s'
+                           % (rel, 'first is %d' % res.info['err_member']
+                              if res.info['err_code'] else 'none'),
+                   'ok': rel < 2e-6},
     }
 
 

@@ -47,7 +47,9 @@ typedef enum {
 enum { PD_EXPLICIT = 0,   /* integrate_explicit,                      basepop.py:658-688      */
        PD_TAU_LEAP = 1,   /* integrate_discrete_time_stochastic,      basepop.py:797-852      */
        PD_GILLESPIE = 2,  /* integrate_continuous_time_stochastic,    basepop.py:737-795      */
-       PD_DIAGNOSTICS = 3 };/* calculate_diagnostics over stored times, basepop.py:911-960    */
+       PD_DIAGNOSTICS = 3,/* calculate_diagnostics over stored times,  basepop.py:911-960     */
+       PD_ADAPTIVE = 4 }; /* integrate(method='scipy'): odeint on the derivative closure,
+                             basepop.py:882-886 -- adaptive Dormand-Prince 5(4) per member     */
 /* output selector */
 enum { PD_FULL = 0,       /* soln [T][C][M] fp64 (the reference's soln_array per member)      */
        PD_FINAL = 1,      /* final state [C][M] fp64                                          */
@@ -161,12 +163,32 @@ typedef struct {
   const double *const *member_param_rows; /* as in pd_stoch_run                                */
 } pd_diag_run;
 
+/* The adaptive integrator (model built with method PD_ADAPTIVE; scale-up functions are traced on
+ * time, so n_scaleup is 0).  Replaces `odeint(derivative, y, self.target_times)`,
+ * basepop.py:886: the state of every member at every target time, local error controlled by
+ * rtol / atol (odeint's defaults are 1.49012e-8 for both).                                     */
+typedef struct {
+  int64_t n_member, member0;
+  const double *y0; int32_t y0_per_member, n_time;
+  const double *uniform_params;   /* [n_param] HOST                                           */
+  const double *member_params;    /* [n_member_param][M]                                      */
+  const double *const *member_param_rows; /* as in pd_stoch_run                               */
+  const double *target_times;     /* [n_time] HOST, increasing                                */
+  double rtol, atol;
+  double first_step;              /* 0: estimated per member                                  */
+  int64_t max_steps;              /* attempted-step budget per member (PD_ERR_MAX_STEPS)      */
+  double *soln;                   /* PD_FULL  [T][C][M]                                       */
+  double *final_state;            /* PD_FINAL [C][M]                                          */
+  void *stream;
+} pd_adaptive_run;
+
 /* ---- library ---------------------------------------------------------------------------- */
 int pd_version(void);
 const char *pd_last_error(void);
 int pd_device_count(void);
 /* sizeof() of the ABI structs as compiled: 0 pd_model_desc, 1 pd_run_result, 2 pd_stoch_run,
- * 3 pd_explicit_run, 4 pd_diag_run -- lets a foreign-language binding verify its struct layout.              */
+ * 3 pd_explicit_run, 4 pd_diag_run, 5 pd_adaptive_run -- lets a foreign-language binding verify
+ * its struct layout.                                                                           */
 int pd_struct_size(int which);
 
 /* ---- flow compiler back end -------------------------------------------------------------- */
@@ -191,6 +213,9 @@ int pd_explicit_schedule(int32_t n_time, const double *target_times, double min_
 int pd_run_explicit(pd_model *m, const pd_explicit_run *run, pd_run_result *res);
 int pd_run_tau_leap(pd_model *m, const pd_stoch_run *run, pd_run_result *res);
 int pd_run_gillespie(pd_model *m, const pd_stoch_run *run, pd_run_result *res);
+/* replaces the odeint call of integrate(method='scipy') (basepop.py:882-886) for a batch of
+ * members; pd_run_result.n_steps = attempted steps, total */
+int pd_run_adaptive(pd_model *m, const pd_adaptive_run *run, pd_run_result *res);
 /* replaces BaseModel.calculate_diagnostics (basepop.py:911-960) for a batch of members */
 int pd_run_diagnostics(pd_model *m, const pd_diag_run *run, pd_run_result *res);
 

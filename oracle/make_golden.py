@@ -103,6 +103,28 @@ def main():
     m = strains(); m.make_times(0, 200, 1); m.integrate('explicit')
     out['strains_explicit'] = m.soln_array
 
+    # ---- integrate('scipy'): scipy.integrate.odeint (LSODA) on the derivative closure --------
+    # (basepop.py:882-886).  Not reproducible bit for bit by another solver: these pin the
+    # adaptive device integrator within the tolerance stated in DESIGN.md.
+    import scipy.integrate  # noqa: F401  (the reference checks sys.modules for 'scipy')
+    m = sir(); m.make_times(0, 50, 1); m.integrate('scipy')
+    out['sir_odeint'] = m.soln_array
+    m = seir['SeirModel'](SEIR['measles']); m.make_times(0, 200, 1); m.integrate('scipy')
+    out['seir_measles_odeint'] = m.soln_array
+    # SEIR with demography: only the first 300 days.  Over longer horizons (2000 days, the 50
+    # years of config 2) LSODA evaluates the derivative on a slightly negative internal state
+    # between epidemic waves and the reference's own checks() assert (basepop.py:623 -> :1025)
+    # aborts integrate('scipy') with AssertionError.
+    m = seir['SeirDemographyModel'](SEIR['measles']); m.make_times(0, 300, 1)
+    m.integrate('scipy')
+    out['seird_odeint_300'] = m.soln_array
+    m = tb([]); m.make_times(1900, 2050, .05); m.integrate(method='scipy')
+    out['tb_odeint_every50'] = m.soln_array[::50]
+    m = rmit(RMIT); m.set_param('beta', 50.); m.make_times(0, 100., 1.); m.integrate('scipy')
+    out['rmit_odeint_100'] = m.soln_array
+    m = strains(); m.make_times(0, 200, 1); m.integrate('scipy')
+    out['strains_odeint'] = m.soln_array
+
     # ---- is_continue chain (numpy.float64 state -> naive sum path) -----------------------
     m = mix({'start_population': 100}); m.make_times(0, 5, 0.2); m.integrate('explicit')
     m.make_times(5, 10, 0.2); m.integrate('explicit', is_continue=True)

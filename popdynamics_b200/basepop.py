@@ -14,6 +14,8 @@ assertion behaviour and result attributes.  What changed is everything behind
       -> NVRTC-specialised sm_100a kernels (popdynamics_b200/csrc/kernels/*.cuh)
 
 There is no CPU fallback: without the CUDA extension or without a GPU ``integrate`` raises.
+``integrate('scipy')`` runs an adaptive Runge-Kutta integrator on the device in place of
+``scipy.integrate.odeint`` (basepop.py:882-886).
 
 Additive API (not in the reference): ``set_param`` / ``set_compartment`` also accept 1-D
 ``numpy.ndarray`` values (one entry per ensemble member), and ``integrate_ensemble`` runs
@@ -404,21 +406,98 @@ class BaseModel(object):
             assert label in connected, \
                 'Compartment "%s" doesn\'t have any entry or transfer flows' % label
 
+    # ------------------------------------------------------------------ host restatements
+    def make_derivate_fn(self):
+        """The derivative closure ``f(y, t)`` of basepop.py:613-626, on the HOST: time and
+        compartments are loaded, ``prepare_vars_and_flows`` runs, ``checks`` asserts, the flow
+        vector comes back in label order.  The device integrators use the compiled form of the
+        same chain (``pd_derivative``); this closure is what scripts pass to their own solvers
+        and what the tests feed to ``scipy.integrate.odeint``."""
+        def derivative_fn(y, t):
+            self.time = t
+            self.compartments = self.convert_list_to_compartments(y)
+            self.prepare_vars_and_flows()
+            flow_vector = self.convert_compartments_to_list(self.flows)
+            self.checks()
+            return flow_vector
+
+        derivative_fn.pd_model = self
+        return derivative_fn
+
+    def calculate_events(self):
+        """``self.events``: the list of ``(from_label, to_label, rate)`` the stochastic loops draw
+        from, in flow-table order (basepop.py:690-735).  Entry events are always present, the
+        others only with a positive rate; the two death totals are side outputs.  Host version of
+        what the kernels evaluate per step (``PD_FOR_EACH_LIVE_ROW``)."""
+        events = []
+        for label, var_label in self.var_entry_rate_flow:
+            events.append((None, label, self.vars[var_label]))
+        transfers = [(f, t, self.vars[v]) for f, t, v in self.var_transfer_rate_flows]
+        transfers += list(self.fixed_transfer_rate_flows)
+        for from_label, to_label, rate in transfers:
+            val = self.compartments[from_label] * rate
+            if val > 0:
+                events.append((from_label, to_label, val))
+        deaths = [('rate_death', [(label, self.background_death_rate) for label in self.labels]),
+                  ('rate_infection_death', list(self.infection_death_rate_flows))]
+        for total_label, rows in deaths:
+            self.vars[total_label] = 0.
+            for label, rate in rows:
+                val = self.compartments[label] * rate
+                if val > 0:
+                    self.vars[total_label] += val
+                    events.append((label, None, val))
+        self.events = events
+
     # ------------------------------------------------------------------ integrate (device)
+    def _run_on_device(self, y, method, is_continue, **options):
+        from . import ensemble
+        info = ensemble.integrate_single(self, y, method, is_continue, **options)
+        self.last_run_info = info
+        self.soln_array = info['soln']
+        return info
+
+    def integrate_explicit(self, y, derivative=None, min_dt=0.05):
+        """basepop.py:658-688 on the device: explicit Euler from ``y`` over ``target_times`` with
+        sub-step ``min_dt``, filling ``soln_array``.  ``derivative`` is accepted for signature
+        compatibility and must be a closure of THIS model made by ``make_derivate_fn`` (or None):
+        the device integrates the model's compiled derivative, so a foreign function cannot be
+        honoured and is rejected instead of being silently ignored."""
+        if derivative is not None and getattr(derivative, 'pd_model', None) is not self:
+            raise TypeError('integrate_explicit runs the compiled derivative of this model on the '
+                            'device; pass make_derivate_fn() of the same model (or None)')
+        return self._run_on_device(y, 'explicit', getattr(self, '_continuing', False),
+                                   min_dt=min_dt)
+
+    def integrate_continuous_time_stochastic(self, y):
+        """basepop.py:737-795 on the device (Gillespie direct method)."""
+        return self._run_on_device(y, 'continuous_time_stochastic',
+                                   getattr(self, '_continuing', False))
+
+    def integrate_discrete_time_stochastic(self, y):
+        """basepop.py:797-852 on the device (clamped Poisson tau-leap)."""
+        return self._run_on_device(y, 'discrete_time_stochastic',
+                                   getattr(self, '_continuing', False))
+
+    def integrate_adaptive(self, y, rtol=1.49012e-8, atol=1.49012e-8):
+        """What ``integrate('scipy')`` runs: the adaptive Dormand-Prince 5(4) integrator on the
+        device, in place of ``odeint(derivative, y, self.target_times)`` (basepop.py:886)."""
+        return self._run_on_device(y, 'scipy', getattr(self, '_continuing', False),
+                                   rtol=rtol, atol=atol)
+
     def integrate(self, method='explicit', is_continue=False):
         """
-        Drop-in for basepop.py:854-903.  ``method`` is one of ``'explicit'``,
-        ``'continuous_time_stochastic'``, ``'discrete_time_stochastic'``; ``'scipy'`` (LSODA in a
-        third-party Fortran library, basepop.py:882-886) is rejected.  Runs one ensemble member
-        on the GPU and fills ``soln_array``, ``times`` and the diagnostics exactly like the
-        reference.
+        Drop-in for basepop.py:854-903.  ``method`` is one of ``'explicit'``, ``'scipy'``,
+        ``'continuous_time_stochastic'``, ``'discrete_time_stochastic'``.  Runs one ensemble
+        member on the GPU through the per-method entry points above (so a subclass that overrides
+        one of them is honoured) and fills ``soln_array``, ``times`` and the diagnostics exactly
+        like the reference.  ``'scipy'`` does not need scipy: LSODA is replaced by an adaptive
+        Runge-Kutta pair with the same default tolerances (agreement within 1e-5 relative, not
+        bit for bit; DESIGN.md).
         """
         assert bool(self.target_times), 'Haven\'t set times yet'
-        if method == 'scipy':
-            raise NotImplementedError(
-                "method='scipy' (scipy.integrate.odeint) is outside the B200 hot path; "
-                "use 'explicit', 'continuous_time_stochastic' or 'discrete_time_stochastic'")
-        if method not in ('explicit', 'continuous_time_stochastic', 'discrete_time_stochastic'):
+        if method not in ('explicit', 'scipy', 'continuous_time_stochastic',
+                          'discrete_time_stochastic'):
             raise ValueError('unknown integration method %r' % (method,))
 
         if not is_continue:
@@ -429,10 +508,19 @@ class BaseModel(object):
             self.save_soln_array = self.soln_array
             y = self.convert_compartments_to_list(self.compartments)
 
-        from . import ensemble
-        info = ensemble.integrate_single(self, y, method, is_continue)
-        self.last_run_info = info
-        self.soln_array = info['soln']
+        self._continuing = bool(is_continue)
+        try:
+            if method == 'explicit':
+                info = self.integrate_explicit(y, self.make_derivate_fn(), self.explicit_min_dt)
+            elif method == 'scipy':
+                info = self.integrate_adaptive(y)
+            elif method == 'continuous_time_stochastic':
+                info = self.integrate_continuous_time_stochastic(y)
+            else:
+                info = self.integrate_discrete_time_stochastic(y)
+        finally:
+            self._continuing = False
+        info = info if isinstance(info, dict) else (self.last_run_info or {})
 
         if is_continue:
             self.soln_array = numpy.concatenate((self.save_soln_array, self.soln_array[1:]), 0)
@@ -440,10 +528,11 @@ class BaseModel(object):
         else:
             self.times = copy.deepcopy(self.target_times)
 
-        if method == 'explicit':
+        if method in ('explicit', 'scipy'):
             # state the reference leaves in self.vars after its last derivative call: key order
-            # of prepare_vars_and_flows and scale-ups frozen at the last sub-step time
-            # (basepop.py:606-611)
+            # of prepare_vars_and_flows and scale-ups frozen at the last evaluation time
+            # (basepop.py:606-611); for 'scipy' that time is LSODA's
+            # business in the reference and the last target time here
             last_eval_time = info.get('last_eval_time')
             if last_eval_time is not None:
                 self.time = last_eval_time
@@ -452,7 +541,7 @@ class BaseModel(object):
                 self.prepare_vars_and_flows()
         else:
             self.compartments = self.convert_list_to_compartments(
-                [int(v) for v in info['soln'][-1]])
+                [int(v) for v in self.soln_array[-1]])
         self.calculate_diagnostics()
 
     def integrate_ensemble(self, method='explicit', **kwargs):

@@ -16,11 +16,11 @@ import numpy
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libpopdyn_b200.so')
 
-EXPLICIT, TAU_LEAP, GILLESPIE, DIAGNOSTICS = 0, 1, 2, 3
+EXPLICIT, TAU_LEAP, GILLESPIE, DIAGNOSTICS, ADAPTIVE = 0, 1, 2, 3, 4
 FULL, FINAL, STATS = 0, 1, 2
 PHILOX, INJECT = 0, 1
 METHOD_CODES = {'explicit': EXPLICIT, 'discrete_time_stochastic': TAU_LEAP,
-                'continuous_time_stochastic': GILLESPIE}
+                'continuous_time_stochastic': GILLESPIE, 'scipy': ADAPTIVE}
 OUTPUT_CODES = {'full': FULL, 'final': FINAL, 'stats': STATS}
 
 PD_E_NO_DEVICE, PD_E_MODEL = -4, -5
@@ -31,12 +31,15 @@ DEVICE_ERRORS = {
     4: 'injected uniform stream exhausted',
     5: 'log(0) in the Gillespie waiting time',
     6: 'compartment count exceeds the range of the statistics accumulators (2**31)',
+    7: 'adaptive integrator: step budget exhausted (raise max_steps)',
+    8: 'adaptive integrator: step size underflow',
 }
 
 EXPORTED_SYMBOLS = (
     'pd_version', 'pd_last_error', 'pd_device_count', 'pd_struct_size', 'pd_model_create', 'pd_model_destroy',
     'pd_model_cubin_size', 'pd_model_cubin_copy', 'pd_explicit_schedule', 'pd_run_explicit',
-    'pd_run_tau_leap', 'pd_run_gillespie', 'pd_run_diagnostics', 'pd_hist_quantiles',
+    'pd_run_tau_leap', 'pd_run_gillespie', 'pd_run_diagnostics', 'pd_run_adaptive',
+    'pd_hist_quantiles',
     'pd_hist_moments', 'pd_philox_fill', 'pd_microbench')
 
 
@@ -105,6 +108,16 @@ class DiagRun(C.Structure):
                 ('member_param_rows', C.c_void_p)]
 
 
+class AdaptiveRun(C.Structure):
+    _fields_ = [('n_member', C.c_int64), ('member0', C.c_int64),
+                ('y0', C.c_void_p), ('y0_per_member', C.c_int32), ('n_time', C.c_int32),
+                ('uniform_params', C.c_void_p), ('member_params', C.c_void_p),
+                ('member_param_rows', C.c_void_p), ('target_times', C.c_void_p),
+                ('rtol', C.c_double), ('atol', C.c_double), ('first_step', C.c_double),
+                ('max_steps', C.c_int64), ('soln', C.c_void_p), ('final_state', C.c_void_p),
+                ('stream', C.c_void_p)]
+
+
 _lib = None
 
 
@@ -136,6 +149,7 @@ def lib():
     L.pd_run_tau_leap.argtypes = [C.c_void_p, P(StochRun), P(RunResult)]
     L.pd_run_gillespie.argtypes = [C.c_void_p, P(StochRun), P(RunResult)]
     L.pd_run_diagnostics.argtypes = [C.c_void_p, P(DiagRun), P(RunResult)]
+    L.pd_run_adaptive.argtypes = [C.c_void_p, P(AdaptiveRun), P(RunResult)]
     L.pd_hist_quantiles.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     L.pd_hist_moments.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
@@ -229,7 +243,7 @@ def run(model, run_struct):
     caller decides which Python exception it maps to."""
     res = RunResult()
     fn = {EXPLICIT: lib().pd_run_explicit, TAU_LEAP: lib().pd_run_tau_leap,
-          GILLESPIE: lib().pd_run_gillespie,
+          GILLESPIE: lib().pd_run_gillespie, ADAPTIVE: lib().pd_run_adaptive,
           DIAGNOSTICS: lib().pd_run_diagnostics}[model.desc.method]
     status = fn(model.handle, C.byref(run_struct), C.byref(res))
     if status != 0 and status != PD_E_MODEL:

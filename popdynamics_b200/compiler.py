@@ -26,6 +26,7 @@ import contextlib
 import hashlib
 import math
 import numbers
+import sys
 
 import numpy
 
@@ -501,8 +502,13 @@ class _Tracer(object):
 def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=False,
                   want_vars=None):
     """Lower ``model`` for ``method`` ('explicit', 'discrete_time_stochastic',
-    'continuous_time_stochastic').  ``model.set_flows()`` must already have run
+    'continuous_time_stochastic', 'scipy').  ``model.set_flows()`` must already have run
     (``check_flow_transfers``, basepop.py:638-656).
+
+    'scipy' (basepop.py:882-886: ``odeint`` on the derivative closure) is the explicit lowering
+    with two differences: every member is at its own time, so the scale-up closures are traced on
+    the symbolic time instead of tabulated per sub-step; and the state arrives as a numpy array,
+    i.e. ``numpy.float64`` compartments, over which Python's ``sum`` folds plainly.
 
     ``diagnostics=True`` lowers the diagnostics pass instead (``calculate_diagnostics``,
     basepop.py:911-960): at every stored time the compartments are the ``numpy.float64`` values
@@ -514,13 +520,15 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
     feeds none of them is eliminated from the device code."""
     from .basepop import BaseModel
 
-    integer_state = method != 'explicit' and not diagnostics
-    if diagnostics:
+    integer_state = method not in ('explicit', 'scipy') and not diagnostics
+    if diagnostics or method == 'scipy':
         naive_sum = True
     if naive_sum is None:
         # after is_continue the compartments are numpy.float64 (basepop.py:932-933) and Python's
         # sum() falls off its compensated float fast path
         naive_sum = bool(is_continue) and not integer_state
+    if sys.version_info < (3, 12):
+        naive_sum = True          # builtin sum() compensates float sums from CPython 3.12 on
     tr = _Tracer(model, integer_state)
     g = tr.g
     cm = CompiledModel()
@@ -541,6 +549,11 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
         # prepare_vars_and_flows: vars.clear(); scale-ups; calculate_vars (basepop.py:606-610)
         cm.su_labels = list(model.scaleup_fns.keys())
         traced_vars = {label: Sym(g, g.add('su', k)) for k, label in enumerate(cm.su_labels)}
+    elif method == 'scipy':
+        # same prologue, the closures traced on the member's own time
+        traced_vars = {label: _trace_scalar_function(g, fn, time_sym,
+                                                     'scale-up function %r' % (label,))
+                       for label, fn in model.scaleup_fns.items()}
     else:
         # the stochastic loops never clear vars nor evaluate scale-ups (basepop.py:763-765,
         # :822-824): whatever is left in self.vars is visible as stale constants

@@ -18,6 +18,7 @@
 #define PD_METHOD_TAU_LEAP 1
 #define PD_METHOD_GILLESPIE 2
 #define PD_METHOD_DIAGNOSTICS 3
+#define PD_METHOD_ADAPTIVE 4
 
 #define PD_MAX_HIST_COMP 64
 
@@ -28,6 +29,8 @@
 #define PD_ERR_STREAM 4        /* injected uniform stream exhausted                              */
 #define PD_ERR_LOG0 5          /* log(0) in the waiting time (math domain error)                 */
 #define PD_ERR_COUNT_RANGE 6   /* count too large for the statistics accumulators                */
+#define PD_ERR_MAX_STEPS 7     /* adaptive solver: step budget of a member exhausted             */
+#define PD_ERR_STEP_SIZE 8     /* adaptive solver: step size underflow (t + h == t)              */
 
 typedef struct {
   long long n_member;          /* members in this launch                                         */
@@ -103,6 +106,27 @@ typedef struct {
   long long pm_ld;             /* row stride (elements) of pm                                    */
   long long out_ld;            /* row stride of soln / final_state                               */
 } PdExplicitArgs;
+
+typedef struct {
+  long long n_member;
+  long long member0;           /* global id of member 0 of this launch (error reports)           */
+  const double *y0;
+  long long y0_stride_c;
+  long long y0_stride_m;
+  const double *pm;            /* per-member parameters [PD_NPM][.]                              */
+  long long pm_ld;
+  const double *target;        /* target times [T]                                               */
+  double *soln;                /* FULL  [T][C][.]                                                */
+  double *final_state;         /* FINAL [C][.]                                                   */
+  long long out_ld;
+  unsigned long long *n_steps; /* attempted steps, total (atomic)                                */
+  int *err;
+  double rtol, atol;           /* error tolerances (odeint's defaults: 1.49012e-8 both)          */
+  double first_step;           /* 0: estimated per member                                        */
+  long long max_steps;         /* attempted-step budget per member                               */
+  int n_time;
+  int pad;
+} PdAdaptiveArgs;
 
 typedef struct {
   long long n_member;

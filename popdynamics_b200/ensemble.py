@@ -204,7 +204,8 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
                  member_offset=0, uniforms=None, device=0, count_bits=64, block=256,
                  hist_bins=0, hist_max=None, hist_times=None, out=None, moments=None,
                  hist=None, member_params=None, y0=None, stream=None, min_dt=None,
-                 min_blocks=0, statistics='host', mask=None, mask_value=0, moments_from='kernel'):
+                 min_blocks=0, statistics='host', mask=None, mask_value=0, moments_from='kernel',
+                 rtol=1.49012e-8, atol=1.49012e-8, first_step=0.0, max_steps=10 ** 7):
     """Launch one compiled model.  Returns an EnsembleResult.  ``out`` / ``moments`` / ``hist`` /
     ``member_params`` / ``y0`` let the caller supply resident (torch CUDA) buffers.
     ``statistics='device'`` keeps the streaming-statistics accumulators (moments, histograms)
@@ -213,7 +214,9 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
     the members with ``mask[m] == mask_value``; the outputs of the others are left untouched.
     ``moments_from='hist'``: with lossless histograms (width-1 bins at every target time) the exact
     moments are derived from them after the launch instead of being reduced inside the kernel; a
-    count that reaches the last bin raises the device error flag (choose a larger ``hist_max``)."""
+    count that reaches the last bin raises the device error flag (choose a larger ``hist_max``).
+    ``rtol`` / ``atol`` / ``first_step`` / ``max_steps`` steer the adaptive integrator
+    (``method='scipy'``; the defaults are scipy.integrate.odeint's tolerances)."""
     method_code = capi.METHOD_CODES[method]
     out_code = capi.OUTPUT_CODES[output]
     rng_code = capi.INJECT if uniforms is not None else capi.PHILOX
@@ -241,7 +244,7 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
     else:
         y0_per_member = 1 if (y0.ndim == 2) else 0
     param_rows = None
-    if method != 'explicit' and count_bits == 32:
+    if method in ('discrete_time_stochastic', 'continuous_time_stochastic') and count_bits == 32:
         # 32-bit counts: an initial state at or above 2**31 would be silently saturated by the
         # double -> int conversion on the device; numpy / Python ints never wrap
         peak = float(y0.max()) if (y0.numel() if _is_torch(y0) else y0.size) else 0.0
@@ -280,6 +283,19 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
             run.scaleup_table = capi.address(numpy.zeros((1, cm.n_su)))
         run.n_steps = len(dt)
         res.info['last_eval_time'] = float(t_eval[-1]) if len(t_eval) else None
+    elif method == 'scipy':
+        if mask is not None:
+            raise ValueError("a member mask is not supported by method='scipy'")
+        run = capi.AdaptiveRun()
+        run.n_member, run.member0 = M, int(member_offset)
+        run.y0, run.y0_per_member, run.n_time = capi.address(y0), y0_per_member, T
+        run.uniform_params = capi.address(uniform)
+        run.member_params = capi.address(member_params)
+        run.member_param_rows = param_rows[1] if param_rows else None
+        run.target_times = capi.address(tt)
+        run.rtol, run.atol, run.first_step = float(rtol), float(atol), float(first_step)
+        run.max_steps = int(max_steps)
+        res.info['last_eval_time'] = float(tt[-1])
     else:
         run = capi.StochRun()
         run.n_member, run.member0 = M, int(member_offset)
@@ -302,7 +318,7 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
         res.final = out if out is not None else alloc((C, M), numpy.float64)
         run.final_state = capi.address(res.final)
     else:
-        if method == 'explicit':
+        if method in ('explicit', 'scipy'):
             raise ValueError("output='stats' is defined for the stochastic integrators")
         on_device = statistics == 'device'
         if statistics not in ('host', 'device'):
@@ -410,11 +426,12 @@ def raise_device_error(info, method):
         raise ZeroDivisionError(message)       # basepop.py:776
     if code == 5:
         raise ValueError('math domain error: ' + message)
-    raise RuntimeError(message)
+    raise RuntimeError(message)              # 4 stream exhausted, 6 count range, 7 / 8 adaptive
 
 
-def integrate_single(model, y, method, is_continue):
-    """One member, full trajectory: the body of ``BaseModel.integrate``."""
+def integrate_single(model, y, method, is_continue, **options):
+    """One member, full trajectory: the body of ``BaseModel.integrate``.  ``options`` go to
+    ``run_compiled`` (``min_dt`` for the explicit, ``rtol`` / ``atol`` for the adaptive method)."""
     cm = compiler.compile_model(model, method, is_continue=is_continue)
     seed = model.seed if model.seed is not None else random.getrandbits(63)
     # With a fixed model.seed every integrate(is_continue=True) segment gets its OWN Philox
@@ -424,7 +441,7 @@ def integrate_single(model, y, method, is_continue):
     segment = getattr(model, '_segment', 0) + 1 if is_continue else 0
     model._segment = segment
     res = run_compiled(model, cm, method, y, model.target_times, 1, output='full', seed=seed,
-                       member_offset=segment, device=model.device)
+                       member_offset=segment, device=model.device, **options)
     raise_device_error(res.info, method)
     info = dict(res.info)
     info['soln'] = numpy.ascontiguousarray(res.soln[:, :, 0])

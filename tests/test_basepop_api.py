@@ -104,10 +104,45 @@ def test_integrate_preconditions_and_rejections():
     with pytest.raises(AssertionError, match='times'):
         m.integrate()
     m.make_times(0, 5, 1)
-    with pytest.raises(NotImplementedError, match='scipy'):
-        m.integrate('scipy')
     with pytest.raises(ValueError):
         m.integrate('runge_kutta')
+    # a foreign derivative cannot be honoured by the device integrator: rejected loudly
+    with pytest.raises(TypeError, match='make_derivate_fn'):
+        m.integrate_explicit(m.get_init_list(), lambda y, t: [0.] * 3)
+
+
+def test_host_derivative_closure_and_events_match_the_reference_semantics():
+    # make_derivate_fn (basepop.py:613-626): vars cleared, scale-ups, hook, flows, checks
+    m = helpers.make_model('tb')
+    m.check_flow_transfers()
+    f = m.make_derivate_fn()
+    y = [1e6, 10., 20., 30., 4., 5.]
+    flows = f(y, 1975.)
+    assert m.time == 1975. and len(flows) == len(m.labels)
+    assert list(m.vars)[0] == 'program_rate_detect'           # scale-ups first (basepop.py:608)
+    assert 'rate_death' in m.vars and 'rate_infection_death' in m.vars
+    total = sum(y)
+    births = m.params['demo_rate_birth'] * total
+    deaths = m.vars['rate_death'] + m.vars['rate_infection_death']
+    assert abs(sum(flows) - (births - deaths)) < 1e-6
+    with pytest.raises(AssertionError):                       # checks() on a negative state
+        f([-1.] + y[1:], 1975.)
+    # calculate_events (basepop.py:690-735): entry always, others only when positive
+    s = helpers.make_model('strains')
+    s.check_flow_transfers()
+    s.compartments = {k: int(v) for k, v in s.init_compartments.items()}
+    s.calculate_vars()
+    s.calculate_events()
+    assert s.events[0] == (None, 'susceptible', 2)
+    kinds = [(e[0], e[1]) for e in s.events]
+    assert ('susceptible', 'infectious_invader') in kinds
+    assert ('recovered_resident', None) not in kinds          # zero count: no event
+    assert all(e[2] > 0 for e in s.events[1:])
+    assert s.vars['rate_death'] == sum(e[2] for e in s.events if e[1] is None)
+    s.compartments['infectious_invader'] = 0
+    s.calculate_vars()
+    s.calculate_events()
+    assert ('susceptible', 'infectious_invader') not in [(e[0], e[1]) for e in s.events]
 
 
 def test_sigmoid_curves():

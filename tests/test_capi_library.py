@@ -37,8 +37,11 @@ def test_header_constants_match_the_binding():
     assert int(defines['PD_FLAG_HIST_MOMENTS']) == capi.FLAG_HIST_MOMENTS
     enums = dict(re.findall(r'\b(PD_[A-Z_]+)\s*=\s*(-?\d+)', text))
     assert int(enums['PD_DIAGNOSTICS']) == capi.DIAGNOSTICS
+    assert int(enums['PD_ADAPTIVE']) == capi.ADAPTIVE == capi.METHOD_CODES['scipy']
+    assert (int(enums['PD_EXPLICIT']), int(enums['PD_TAU_LEAP']), int(enums['PD_GILLESPIE'])) == \
+        (capi.EXPLICIT, capi.TAU_LEAP, capi.GILLESPIE)
     for name, value in capi.METHOD_CODES.items():
-        assert value in (0, 1, 2)
+        assert value in (0, 1, 2, 4)
     assert int(enums['PD_E_INVALID']) < 0 and int(enums['PD_E_NO_DEVICE']) == capi.PD_E_NO_DEVICE
 
 
@@ -64,7 +67,8 @@ def test_structs_match_the_compiled_layout(built_library):
     assert ctypes.sizeof(capi.StochRun) == size(2)
     assert ctypes.sizeof(capi.ExplicitRun) == size(3)
     assert ctypes.sizeof(capi.DiagRun) == size(4)
-    assert size(5) == -1
+    assert ctypes.sizeof(capi.AdaptiveRun) == size(5)
+    assert size(6) == -1
 
 
 @pytest.mark.skipif(capi.lib().pd_device_count() > 0, reason='a GPU is present')
