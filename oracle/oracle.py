@@ -23,10 +23,10 @@ ERRORS = {0: 'ok', 1: 'checks() failed', 2: 'bad Poisson mean', 3: 'zero total r
 class PdoModel(C.Structure):
     _fields_ = [('n_comp', C.c_int32), ('n_param', C.c_int32), ('n_su', C.c_int32),
                 ('n_ins', C.c_int32), ('n_flow', C.c_int32), ('n_check', C.c_int32),
-                ('pad0', C.c_int32), ('pad1', C.c_int32),
+                ('n_post_check', C.c_int32), ('pad1', C.c_int32),
                 ('ins', C.c_void_p), ('consts', C.c_void_p), ('kind', C.c_void_p),
                 ('frm', C.c_void_p), ('to', C.c_void_p), ('slot', C.c_void_p),
-                ('is_int', C.c_void_p), ('check', C.c_void_p)]
+                ('is_int', C.c_void_p), ('check', C.c_void_p), ('post_check', C.c_void_p)]
 
 
 class PdoRng(C.Structure):
@@ -107,11 +107,13 @@ OPCODE = {name: i for i, name in enumerate(OPS)}
 
 def oracle_program(cm):
     """The traced expression graph of a ``CompiledModel`` as the bytecode the C oracle
-    interprets.  Value slots: [compartments | parameters | time | scale-ups | one per
+    interprets.  Value slots: [compartments | parameters | time | scale-ups | updated
+    compartments (only when a checks() was traced for the stochastic loops) | one per
     instruction]; instructions in the graph's evaluation order (program order of the hook)."""
     g = cm.graph
     C, NP, NSU = cm.n_comp, cm.n_param, cm.n_su
-    base = C + NP + 1 + NSU
+    post = list(getattr(cm, 'post_check_nodes', []))
+    base = C + NP + 1 + NSU + (C if post else 0)
     slot_of, ins, consts = {}, [], []
     for n in cm.order:
         node = g.nodes[n]
@@ -124,6 +126,8 @@ def oracle_program(cm):
             slot_of[n] = C + NP
         elif op == 'su':
             slot_of[n] = C + NP + 1 + node[1]
+        elif op == 'comp2':
+            slot_of[n] = C + NP + 1 + NSU + node[1]
         elif op == 'const':
             consts.append(g.const_values[n])
             slot_of[n] = base + len(ins)
@@ -137,6 +141,7 @@ def oracle_program(cm):
         consts=np.asarray(consts, dtype=np.float64),
         slot=np.asarray([slot_of[n] for n in cm.flow_node], dtype=np.int32),
         check=np.asarray([slot_of[n] for n in cm.check_nodes], dtype=np.int32),
+        post_check=np.asarray([slot_of[n] for n in post], dtype=np.int32),
         n_values=base + len(ins), slot_of=slot_of)
 
 
@@ -149,14 +154,16 @@ class OracleModel(object):
         table = cm.flow_table()
         self._keep = dict(ins=np.ascontiguousarray(prog['ins']), consts=prog['consts'],
                           kind=table['kind'], frm=table['frm'], to=table['to'],
-                          slot=prog['slot'], is_int=table['is_int'], check=prog['check'])
+                          slot=prog['slot'], is_int=table['is_int'], check=prog['check'],
+                          post_check=prog['post_check'])
         k = self._keep
         self.n_values = prog['n_values']
         self.slot_of = prog['slot_of']
         self.struct = PdoModel(cm.n_comp, cm.n_param, cm.n_su, len(k['ins']), cm.n_flow,
-                               len(k['check']), 0, 0, _ptr(k['ins']), _ptr(k['consts']),
-                               _ptr(k['kind']), _ptr(k['frm']), _ptr(k['to']), _ptr(k['slot']),
-                               _ptr(k['is_int']), _ptr(k['check']))
+                               len(k['check']), len(k['post_check']), 0, _ptr(k['ins']),
+                               _ptr(k['consts']), _ptr(k['kind']), _ptr(k['frm']), _ptr(k['to']),
+                               _ptr(k['slot']), _ptr(k['is_int']), _ptr(k['check']),
+                               _ptr(k['post_check']))
         self.C = cm.n_comp
 
     # ---- parameter helpers -------------------------------------------------------------

@@ -249,12 +249,22 @@ static double py_sum(const double *x, const int32_t *is_int, int32_t n) {
 /* ------------------------------------------------------------------------------------------
  * Expression program (the traced calculate_vars hook, basepop.py:553 and its overrides).
  * ---------------------------------------------------------------------------------------- */
-static int n_values(const pdo_model *m) {
-  return m->n_comp + m->n_param + 1 + m->n_su + m->n_ins;
+/* value slots: [compartments | parameters | time | scale-ups | updated compartments (only with
+ * post checks) | one per instruction] */
+static int n_leaves(const pdo_model *m) {
+  return m->n_comp + m->n_param + 1 + m->n_su + (m->n_post_check > 0 ? m->n_comp : 0);
 }
+static int n_values(const pdo_model *m) { return n_leaves(m) + m->n_ins; }
 
 void pdo_eval_vars(const pdo_model *m, const double *y, const double *params, double time,
                    const double *su, double *v) {
+  pdo_eval_vars2(m, y, y, params, time, su, v);
+}
+
+/* y: the compartments the hooks saw (start of the step); y2: the updated compartments a traced
+ * stochastic checks() looks at */
+void pdo_eval_vars2(const pdo_model *m, const double *y, const double *y2, const double *params,
+                    double time, const double *su, double *v) {
   int base = 0;
   for (int i = 0; i < m->n_comp; i++) v[base + i] = y[i];
   base += m->n_comp;
@@ -263,6 +273,10 @@ void pdo_eval_vars(const pdo_model *m, const double *y, const double *params, do
   v[base++] = time;
   for (int i = 0; i < m->n_su; i++) v[base + i] = su ? su[i] : 0.0;
   base += m->n_su;
+  if (m->n_post_check > 0) {
+    for (int i = 0; i < m->n_comp; i++) v[base + i] = y2[i];
+    base += m->n_comp;
+  }
   for (int k = 0; k < m->n_ins; k++) {
     const int32_t *in = m->ins + 4 * k;
     double a = 0, b = 0, c = 0, r = 0;
@@ -296,6 +310,17 @@ void pdo_eval_vars(const pdo_model *m, const double *y, const double *params, do
     }
     v[base + k] = r;
   }
+}
+
+/* a user-defined checks() in the stochastic loops: 1 when an assertion fails */
+static int run_post_checks(const pdo_model *m, const int64_t *y_new, const double *y_old,
+                           const double *params, double time, double *v, double *scratch) {
+  if (m->n_post_check <= 0) return 0;
+  for (int i = 0; i < m->n_comp; i++) scratch[i] = (double)y_new[i];
+  pdo_eval_vars2(m, y_old, scratch, params, time, 0, v);
+  for (int k = 0; k < m->n_post_check; k++)
+    if (!(v[m->post_check[k]] != 0.0)) return 1;
+  return 0;
 }
 
 static int run_checks(const pdo_model *m, const double *v) {
@@ -443,6 +468,7 @@ int64_t pdo_tau_leap(const pdo_model *m, const double *y0, const double *params,
   const int C = m->n_comp, S = m->n_flow;
   double *v = (double *)malloc(sizeof(double) * (size_t)n_values(m));
   double *yd = (double *)malloc(sizeof(double) * (size_t)C);
+  double *y2 = (double *)malloc(sizeof(double) * (size_t)C);
   int64_t *y = (int64_t *)malloc(sizeof(int64_t) * (size_t)C);
   int32_t *ev_flow = (int32_t *)malloc(sizeof(int32_t) * (size_t)(S + 1));
   int32_t *ev_int = (int32_t *)malloc(sizeof(int32_t) * (size_t)(S + 1));
@@ -471,13 +497,14 @@ int64_t pdo_tau_leap(const pdo_model *m, const double *y0, const double *params,
       }
     }
     for (int i = 0; i < C; i++) if (!(y[i] >= 0) && !e) e = 1;      /* :846 */
+    if (!e && run_post_checks(m, y, yd, params, time, v, y2)) e = 1;  /* :846, user-defined */
     time += dt;                                                     /* :848 */
     if (soln) for (int i = 0; i < C; i++) soln[(size_t)it * C + i] = (double)y[i]; /* :850-852 */
     n_step++;
   }
   if (rng->exhausted && !e) e = 4;
   if (!soln) for (int i = 0; i < C; i++) yd[i] = (double)y[i];
-  free(v); free(yd); free(y); free(ev_flow); free(ev_int); free(ev_rate);
+  free(v); free(yd); free(y2); free(y); free(ev_flow); free(ev_int); free(ev_rate);
   if (err) *err = e;
   return n_step;
 }
@@ -489,6 +516,7 @@ int64_t pdo_gillespie(const pdo_model *m, const double *y0, const double *params
   const int C = m->n_comp, S = m->n_flow;
   double *v = (double *)malloc(sizeof(double) * (size_t)n_values(m));
   double *yd = (double *)malloc(sizeof(double) * (size_t)C);
+  double *y2 = (double *)malloc(sizeof(double) * (size_t)C);
   int64_t *y = (int64_t *)malloc(sizeof(int64_t) * (size_t)C);
   int32_t *ev_flow = (int32_t *)malloc(sizeof(int32_t) * (size_t)(S + 1));
   int32_t *ev_int = (int32_t *)malloc(sizeof(int32_t) * (size_t)(S + 1));
@@ -519,13 +547,15 @@ int64_t pdo_gillespie(const pdo_model *m, const double *y0, const double *params
         if (from >= 0) y[from] -= 1;                                /* :778-787 */
         if (to >= 0) y[to] += 1;
         for (int i = 0; i < C; i++) if (!(y[i] >= 0) && !e) e = 1;  /* :789 */
+        if (!e && run_post_checks(m, y, yd, params, time, v, y2)) e = 1;
         n_event++;
+        if (e) break;
       }
       time += dt;                                                   /* :790 */
     }
     for (int i = 0; i < C; i++) soln[(size_t)it * C + i] = (double)y[i]; /* :793-795 */
   }
-  free(v); free(yd); free(y); free(ev_flow); free(ev_int); free(ev_rate);
+  free(v); free(yd); free(y2); free(y); free(ev_flow); free(ev_int); free(ev_rate);
   if (err) *err = e;
   return n_event;
 }

@@ -39,7 +39,7 @@ enum {
 enum { PDO_ENTRY = 0, PDO_VAR = 1, PDO_FIXED = 2, PDO_BGDEATH = 3, PDO_INFDEATH = 4 };
 
 typedef struct {
-  int32_t n_comp, n_param, n_su, n_ins, n_flow, n_check, pad0, pad1;
+  int32_t n_comp, n_param, n_su, n_ins, n_flow, n_check, n_post_check, pad1;
   const int32_t *ins;    /* n_ins x 4: op, a, b, c (slot indices)                          */
   const double *consts;
   const int32_t *kind;   /* per flow                                                       */
@@ -49,6 +49,10 @@ typedef struct {
   const int32_t *is_int; /* per flow: 1 when the Python value of the rate is an int (only
                             possible for entry flows); steers Python's sum() path, :775    */
   const int32_t *check;  /* value slots that must be non-zero (traced checks() asserts)    */
+  const int32_t *post_check; /* n_post_check value slots of a user-defined checks() traced for
+                            the stochastic loops (basepop.py:789, :846): evaluated AFTER the
+                            update, on the updated compartments (a second set of n_comp leaf
+                            slots behind the scale-ups) and the vars of the step's start       */
 } pdo_model;
 
 /* ---- uniform sources -------------------------------------------------------------------- */
@@ -89,6 +93,8 @@ int64_t pdo_tau_leap(const pdo_model *m, const double *y0, const double *params,
 int64_t pdo_gillespie(const pdo_model *m, const double *y0, const double *params,
                       int32_t n_time, const double *target, pdo_rng *rng,
                       double *soln, int32_t *err);
+void pdo_eval_vars2(const pdo_model *m, const double *y, const double *y2, const double *params,
+                    double time, const double *su, double *v);
 void pdo_eval_vars(const pdo_model *m, const double *y, const double *params, double time,
                    const double *su, double *values);
 

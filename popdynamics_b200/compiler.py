@@ -49,7 +49,8 @@ class TraceError(TypeError):
 
 class Graph(object):
     """Hash-consed expression DAG.  Node = (op, a, b, c); leaves are ('comp', i), ('param', j),
-    ('time',), ('su', k), ('const', repr)."""
+    ('time',), ('su', k), ('const', repr) and ('comp2', i): compartment i AFTER the update of a
+    stochastic step, seen only by a traced checks()."""
 
     def __init__(self):
         self.nodes = []
@@ -418,6 +419,7 @@ class CompiledModel(object):
         self.flow_is_int = []
         self.flow_names = []
         self.check_nodes = []
+        self.post_check_nodes = [] # user-defined checks() of the stochastic loops (after update)
         self.uses_time = False
         self.var_nodes = {}        # var label -> node id (all vars seen in the trace)
         self.diagnostics = False   # compiled for the diagnostics pass (basepop.py:911-960)
@@ -662,11 +664,18 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
                 cm.check_nodes = []       # integer counts never go negative (clamped draws)
         else:
             if integer_state:
-                raise TraceError(
-                    'a user-defined checks() is only lowered for the explicit integrator; the '
-                    'stochastic integrators keep the default non-negativity invariant')
-            # vars visible to checks(): calculate_flows has also defined the two death totals
-            rate_death, rate_inf = _death_totals(cm, g, comps, bg_sym, inf_syms)
+                # The stochastic loops call checks() AFTER the update of a step / an event
+                # (basepop.py:789, :846): it sees the UPDATED integer compartments (a second set
+                # of leaves, 'comp2'), while self.vars still holds what calculate_vars and
+                # calculate_events left at the start of the step -- including the two death
+                # totals, which calculate_events accumulates over positive terms only (:724-735).
+                rate_death, rate_inf = _death_totals(cm, g, comps, bg_sym, inf_syms,
+                                                     positive_only=True)
+                model.compartments = {label: Sym(g, g.add('comp2', i), is_int=True)
+                                      for i, label in enumerate(cm.labels)}
+            else:
+                # vars visible to checks(): calculate_flows has also defined the two death totals
+                rate_death, rate_inf = _death_totals(cm, g, comps, bg_sym, inf_syms)
             model.vars['rate_death'] = rate_death
             model.vars['rate_infection_death'] = rate_inf
             g.collect_asserts = True
@@ -675,7 +684,11 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
                     model.checks()
             finally:
                 g.collect_asserts = False
-            cm.check_nodes = list(g.assertions)
+                model.compartments = comps
+            if integer_state:
+                cm.post_check_nodes = list(g.assertions)
+            else:
+                cm.check_nodes = list(g.assertions)
         cm.var_nodes = {k: as_sym(v, 'vars[%r]' % k).n for k, v in hook_vars.items()
                         if isinstance(v, (Sym, numbers.Real)) and not getattr(v, 'is_bool', False)}
 
@@ -731,7 +744,7 @@ def params_read_by(cm, roots):
         node = g.nodes[n]
         if node[0] == 'param':
             slots.add(node[1])
-        elif node[0] not in ('comp', 'time', 'su', 'const'):
+        elif node[0] not in ('comp', 'comp2', 'time', 'su', 'const'):
             stack.extend(x for x in node[1:] if x >= 0)
     return slots
 
@@ -741,8 +754,8 @@ def live_order(cm):
     checks and (diagnostics pass) the requested vars / net flows, in creation order, which is
     topological."""
     g = cm.graph
-    roots = list(cm.flow_node) + list(cm.check_nodes) + list(cm.diag_nodes) + \
-        list(cm.diag_flow_nodes)
+    roots = list(cm.flow_node) + list(cm.check_nodes) + list(cm.post_check_nodes) + \
+        list(cm.diag_nodes) + list(cm.diag_flow_nodes)
     live = set()
     stack = list(roots)
     while stack:
@@ -751,7 +764,7 @@ def live_order(cm):
             continue
         live.add(n)
         node = g.nodes[n]
-        if node[0] not in ('comp', 'param', 'time', 'su', 'const'):
+        if node[0] not in ('comp', 'comp2', 'param', 'time', 'su', 'const'):
             stack.extend(x for x in node[1:] if x >= 0)
     return [n for n in range(len(g.nodes)) if n in live]
 
@@ -762,16 +775,26 @@ def _same(a, b):
     return a == b
 
 
-def _death_totals(cm, g, comps, bg_sym, inf_syms):
+def _death_totals(cm, g, comps, bg_sym, inf_syms, positive_only=False):
     """vars['rate_death'] / vars['rate_infection_death'] as calculate_flows accumulates them
-    (basepop.py:587-598)."""
+    (basepop.py:587-598), or -- ``positive_only`` -- as calculate_events does, where a term only
+    counts when it is positive (basepop.py:724-735)."""
+    def add(total, val):
+        if not positive_only or not isinstance(val, Sym):
+            return total + val
+        grown = total + val
+        if not isinstance(total, Sym):
+            total = Sym(g, g.const(float(total)))
+        cond = g.add('gt', val.n, g.const(0.0))
+        return Sym(g, g.add('select', cond, grown.n, total.n))
+
     rate_death = 0.
     if bg_sym is not None:
         for label in cm.labels:
-            rate_death = rate_death + comps[label] * bg_sym
+            rate_death = add(rate_death, comps[label] * bg_sym)
     rate_inf = 0.
     for label, sym in inf_syms:
-        rate_inf = rate_inf + comps[label] * sym
+        rate_inf = add(rate_inf, comps[label] * sym)
     return rate_death, rate_inf
 
 

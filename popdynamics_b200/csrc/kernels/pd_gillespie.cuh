@@ -167,6 +167,15 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
 #undef PD_G3_ENTRY
 #undef PD_G3_TRANSFER
 #undef PD_G3_DEATH
+#if PD_HAS_STEP_CHECKS
+  {
+    /* a user-defined checks() (:789): the updated counts, the vars computed before the event */
+    double y2[PD_C];
+#pragma unroll
+    for (int c = 0; c < PD_C; ++c) y2[c] = (double)y[c];
+    if (!pd_step_checks(yd, y2, U, pm, time, (const double *)0)) return PD_ERR_CHECKS;
+  }
+#endif
   time += dt;                                   /* :790 */
   ++n_event;
   return 0;

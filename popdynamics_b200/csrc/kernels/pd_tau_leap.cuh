@@ -157,7 +157,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   if (PD_EPOCH == 1 || a.n_time == 1) pd_stats_part_flush(a, s_acc, 0, 1);
 #endif
 
-  int bad = 0;
+  int bad = 0, bad_at = 0;
   double time = a.target[0];
   for (int it = 1; it < a.n_time; ++it) {
     if (active) {
@@ -294,6 +294,18 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #undef PD_TAU_DEATH
 #undef PD_TAU_TAKE
         if (sizeof(pd_count) == 4 && signs < 0 && !bad) bad = PD_ERR_COUNT_RANGE;
+#if PD_HAS_STEP_CHECKS
+        {
+          /* a user-defined checks() (:846): the updated counts, the vars of the step's start */
+          double y2[PD_C];
+#pragma unroll
+          for (int c = 0; c < PD_C; ++c) y2[c] = (double)y[c];
+          if (!pd_step_checks(yd, y2, U, pm, time, (const double *)0) && !bad) {
+            bad = PD_ERR_CHECKS;
+            bad_at = it;
+          }
+        }
+#endif
       }
       time += dt;                                           /* :848 */
 #if PD_OUT_MODE == PD_OUT_FULL
@@ -320,7 +332,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
     for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * a.out_ld + m] = (double)y[c];
 #endif
     if (!bad && rng.exhausted) bad = PD_ERR_STREAM;
-    if (bad) pd_raise(a.err, bad, a.member0 + m, 0);
+    if (bad) pd_raise(a.err, bad, a.member0 + m, bad_at);
   }
   if (a.n_steps && active) {
     /* whichever lanes arrive together elect one of them; the groups' counts add up */

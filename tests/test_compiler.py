@@ -137,8 +137,51 @@ def test_custom_checks_are_traced_into_device_assertions():
     assert err == 0
     _, _, err = om.explicit([10., 5.], m.target_times)
     assert err == 1
-    with pytest.raises(TraceError):
-        helpers.compiled(Checked(lambda s: s.params['k']), 'continuous_time_stochastic')
+
+
+def test_custom_checks_in_the_stochastic_loops_see_the_updated_counts_and_the_old_vars():
+    # basepop.py:789 / :846: checks() runs after the update; self.vars is what calculate_vars and
+    # calculate_events left at the START of the step (incl. the positive-only death totals)
+    class Draining(_Weird):
+        def __init__(self, floor):
+            _Weird.__init__(self, lambda s: s.params['k'])
+            self.floor = floor
+            self.set_param('mu', 0.01)
+
+        def set_flows(self):
+            _Weird.set_flows(self)
+            self.set_background_death_rate('mu')
+
+        def calculate_vars(self):
+            _Weird.calculate_vars(self)
+            self.vars['a_before'] = self.compartments['a']
+
+        def checks(self, error_margin=0.1):
+            assert self.compartments['a'] >= self.floor          # updated count
+            assert self.vars['a_before'] >= self.compartments['a']   # old var vs new count
+            assert self.vars['rate_death'] <= 0.2                # calculate_events side output
+
+    for method in ('discrete_time_stochastic', 'continuous_time_stochastic'):
+        cm = helpers.compiled(Draining(0.), method)
+        assert len(cm.post_check_nodes) == 3 and cm.check_nodes == []
+        assert '#define PD_HAS_STEP_CHECKS 1' in cm.cuda_source()
+        assert 'y2[0]' in cm.cuda_source()
+        m = Draining(0.)
+        m.make_times(0, 6, 1)
+        fn = oracle.OracleModel(cm).tau_leap if method.startswith('discrete') else \
+            oracle.OracleModel(cm).gillespie
+        soln, _, err = fn([10., 0.], m.target_times, oracle.Rng('philox', seed=3, member=1))
+        assert err == 0 and soln[-1, 0] < 10
+        # a floor the draining compartment must cross: the assertion fires
+        cm = helpers.compiled(Draining(8.), method)
+        _, _, err = oracle.OracleModel(cm).tau_leap(
+            [10., 0.], m.target_times, oracle.Rng('philox', seed=3, member=1)) \
+            if method.startswith('discrete') else oracle.OracleModel(cm).gillespie(
+                [10., 0.], m.target_times, oracle.Rng('philox', seed=3, member=1))
+        assert err == 1
+    # the default checks() stays free for integer counts
+    cm = helpers.compiled(_Weird(lambda s: s.params['k']), 'discrete_time_stochastic')
+    assert cm.post_check_nodes == [] and '#define PD_HAS_STEP_CHECKS 0' in cm.cuda_source()
 
 
 def test_explicit_schedule_host_logic():

@@ -623,3 +623,39 @@ def test_batched_diagnostics_final_state_sweep_and_stale_scaleups(golden):
     diag = ensemble.diagnostics(m, res)
     assert diag.var_labels == list(golden['tb_var_labels'])
     assert np.array_equal(diag.vars[::50, :, 1], golden['tb_var_array_every50'])
+
+
+@pytest.mark.parametrize('method', ['discrete_time_stochastic', 'continuous_time_stochastic'])
+def test_user_defined_checks_run_inside_the_stochastic_kernels(method):
+    # basepop.py:789 / :846: checks() after the update, lowered through the traced-assert
+    # mechanism: updated counts (y2), vars of the step's start; the oracle fires identically
+    class Limited(helpers.models.StrainsModel):
+        limit = 10 ** 6
+
+        def checks(self, error_margin=0.1):
+            assert self.compartments['infectious_invader'] <= self.limit
+            assert self.vars['population'] + 50 >= sum(self.compartments.values())
+            assert self.vars['rate_death'] < 10.
+
+    n, seed = 512, 21
+    m = Limited()
+    m.make_times(0, 60, 1)
+    res = m.integrate_ensemble(method, n_members=n, output='full', seed=seed)
+    plain = helpers.make_model('strains')
+    plain.make_times(0, 60, 1)
+    want = plain.integrate_ensemble(method, n_members=n, output='full', seed=seed)
+    assert np.array_equal(res.soln, want.soln)            # passing checks change nothing
+    Limited.limit = 3
+    m = Limited()
+    m.make_times(0, 60, 1)
+    res = m.integrate_ensemble(method, n_members=n, output='full', seed=seed, check=False)
+    assert res.info['err_code'] == 1
+    bad = int(res.info['err_member'])
+    om = oracle.OracleModel(helpers.compiled(m, method))
+    fn = om.tau_leap if method.startswith('discrete') else om.gillespie
+    _, _, err = fn(m.get_init_list(), m.target_times, oracle.Rng('philox', seed=seed, member=bad))
+    assert err == 1
+    over = want.soln[:, 2, :].max(axis=0) > 3             # members whose invader passes 3
+    assert over[bad] and over.any()
+    with pytest.raises(AssertionError):
+        m.integrate_ensemble(method, n_members=n, output='final', seed=seed)

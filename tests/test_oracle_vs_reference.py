@@ -148,3 +148,40 @@ def test_injected_uniform_protocol_against_the_reference():
     soln, _, err = helpers.oracle_stochastic(m, 'discrete_time_stochastic', rng)
     assert err == 0 and np.array_equal(soln, theirs.soln_array)
     assert rng.consumed == inj.rng.consumed
+
+
+@pytest.mark.parametrize('method,kind', [('discrete_time_stochastic', 'numpy'),
+                                         ('continuous_time_stochastic', 'python')])
+def test_user_defined_checks_in_the_stochastic_loops_fire_like_the_reference(method, kind):
+    # basepop.py:789 / :846: checks() after every event / step, on the updated compartments with
+    # the vars of the step's start.  Same subclass body on both sides, same MT19937 seed.
+    def body(self, error_margin=0.1):
+        assert self.compartments['infectious_invader'] <= self.limit
+        assert self.vars['population'] + 50 >= sum(self.compartments.values())
+        assert self.vars['rate_death'] < 10.
+
+    base = reference.example_classes('stochastic_strains_model.py')['StrainsModel']
+    ours_base = dropin('stochastic_strains_model.py', 'StrainsModel')
+    for limit, expect_failure in ((10 ** 6, False), (0, True)):
+        Theirs = type('Theirs', (base,), {'checks': body, 'limit': limit})
+        Ours = type('Ours', (ours_base,), {'checks': body, 'limit': limit})
+        reference.seed_all(4)
+        theirs = Theirs()
+        theirs.make_times(0, 150, 1)
+        failed = False
+        try:
+            theirs.integrate(method)
+        except AssertionError:
+            failed = True
+        assert failed == expect_failure
+        ours = Ours()
+        ours.make_times(0, 150, 1)
+        ours.check_flow_transfers()
+        cm = compiler.compile_model(ours, method)
+        assert len(cm.post_check_nodes) == 3
+        om = oracle.OracleModel(cm)
+        fn = om.tau_leap if kind == 'numpy' else om.gillespie
+        soln, _, err = fn(ours.get_init_list(), ours.target_times, oracle.Rng(kind, 4))
+        assert (err == 1) == expect_failure
+        if not expect_failure:
+            assert np.array_equal(soln, theirs.soln_array)
