@@ -33,6 +33,7 @@ DEVICE_ERRORS = {
     6: 'compartment count exceeds the range of the statistics accumulators (2**31)',
     7: 'adaptive integrator: step budget exhausted (raise max_steps)',
     8: 'adaptive integrator: step size underflow',
+    9: 'PTRS squeeze and exact acceptance test disagree (PD_PTRS_CHECK build)',
 }
 
 EXPORTED_SYMBOLS = (

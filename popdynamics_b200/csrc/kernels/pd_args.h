@@ -31,6 +31,7 @@
 #define PD_ERR_COUNT_RANGE 6   /* count too large for the statistics accumulators                */
 #define PD_ERR_MAX_STEPS 7     /* adaptive solver: step budget of a member exhausted             */
 #define PD_ERR_STEP_SIZE 8     /* adaptive solver: step size underflow (t + h == t)              */
+#define PD_ERR_SQUEEZE 9       /* PD_PTRS_CHECK builds: squeeze and exact PTRS test disagree     */
 
 typedef struct {
   long long n_member;          /* members in this launch                                         */

@@ -244,6 +244,9 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
           if (rng.exhausted) break;
 #endif
           const pd_i64 k = pd_poisson_ptrs_attempt(-code, u, v);
+#if PD_PTRS_CHECK
+          if (k == -2 && !bad) bad = PD_ERR_SQUEEZE;
+#endif
           if (k >= 0) PD_TAU_NEXT(k)
           continue;
         }

@@ -17,6 +17,7 @@ CUDA tensors (resident in HBM, no copies).  Multi-GPU sharding lives in ``distri
 import ctypes
 import math
 import random
+import re
 
 import numpy
 
@@ -220,11 +221,23 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
     method_code = capi.METHOD_CODES[method]
     out_code = capi.OUTPUT_CODES[output]
     rng_code = capi.INJECT if uniforms is not None else capi.PHILOX
-    if not min_blocks and (method == 'discrete_time_stochastic' or
+    live_rows = cm.n_flow
+    if method == 'discrete_time_stochastic':
+        # model-size limits of the tau-leap kernel, reported here instead of as an NVRTC log
+        live_rows = int(re.search(r'#define PD_LIVE_NROW (\d+)', cm.cuda_source()).group(1))
+        if live_rows > 64:
+            raise ValueError('the tau-leap kernel handles at most 64 flow-table rows that can '
+                             'fire (its live-row mask is one 64-bit word); this model has %d'
+                             % live_rows)
+    if output == 'stats' and cm.n_comp > 64:
+        raise ValueError("output='stats' supports at most 64 compartments (this model has %d); "
+                         "use output='full' or 'final'" % cm.n_comp)
+    if not min_blocks and ((method == 'discrete_time_stochastic' and live_rows <= 24) or
                            (method == 'continuous_time_stochastic' and cm.n_flow <= 16)):
         # measured on B200 (profiles/): the stochastic kernels are fastest at 64 registers per
-        # thread, i.e. 1024 resident threads per SM, whatever the block size; the Gillespie
-        # kernel of a large flow table (TB: 20 rows, 84 registers) is better left uncapped
+        # thread, i.e. 1024 resident threads per SM, whatever the block size; kernels of a large
+        # flow table (TB Gillespie: 20 rows, ~100 registers) are better left uncapped, and a
+        # tau-leap draw list beyond two dozen rows would only spill under the cap
         min_blocks = max(1, 1024 // int(block))
     kernel = _kernel_for(cm, method_code, out_code, rng_code, device, count_bits, block,
                          min_blocks,

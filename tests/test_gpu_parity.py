@@ -656,6 +656,42 @@ def test_user_defined_checks_run_inside_the_stochastic_kernels(method):
     _, _, err = fn(m.get_init_list(), m.target_times, oracle.Rng('philox', seed=seed, member=bad))
     assert err == 1
     over = want.soln[:, 2, :].max(axis=0) > 3             # members whose invader passes 3
-    assert over[bad] and over.any()
+    assert over.any()
+    if method.startswith('discrete'):                     # checked exactly at the stored times
+        assert over[bad]
     with pytest.raises(AssertionError):
         m.integrate_ensemble(method, n_members=n, output='final', seed=seed)
+
+
+def test_ptrs_squeeze_never_disagrees_with_the_exact_acceptance_test(monkeypatch):
+    # pd_common.cuh: the slow PTRS acceptance test is decided by a certified squeeze; a build with
+    # PD_PTRS_CHECK evaluates BOTH for every slow test and raises error 9 on any disagreement.
+    # Means from 10 to ~1e7 (population swept over six decades), ~1e8 slow tests.
+    n = 1 << 17
+    pop = np.round(10 ** np.random.default_rng(8).uniform(2.5, 8.5, n))
+    def build():
+        m = helpers.make_model('sir', params={'population': pop, 'start_infectious': 20.})
+        m.make_times(0, 120, 1)
+        return m
+    plain = build().integrate_ensemble('discrete_time_stochastic', n_members=n, output='final',
+                                       seed=77)
+    monkeypatch.setenv('POPDYN_DEFINE', '-DPD_PTRS_CHECK=1')
+    ensemble.clear_kernel_cache()
+    checked = build().integrate_ensemble('discrete_time_stochastic', n_members=n, output='final',
+                                         seed=77, check=False)
+    monkeypatch.setenv('POPDYN_DEFINE', '-DPD_PTRS_SQUEEZE=0')
+    ensemble.clear_kernel_cache()
+    exact = build().integrate_ensemble('discrete_time_stochastic', n_members=n, output='final',
+                                       seed=77)
+    monkeypatch.delenv('POPDYN_DEFINE')
+    ensemble.clear_kernel_cache()
+    assert checked.info['err_code'] == 0
+    assert np.array_equal(plain.final, exact.final) and np.array_equal(plain.final, checked.final)
+    m = build()
+    om = oracle.OracleModel(helpers.compiled(m, 'discrete_time_stochastic'))
+    for i in (0, 4097, n - 1):
+        want, _, err = om.tau_leap([v[i] if isinstance(v, np.ndarray) else v
+                                    for v in m.get_init_list()], m.target_times,
+                                   oracle.Rng('philox', seed=77, member=i),
+                                   params=om.member_params(i))
+        assert err == 0 and np.array_equal(plain.final[:, i], want[-1]), i

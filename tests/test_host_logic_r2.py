@@ -154,3 +154,26 @@ def test_reference_runner_loads_the_compiled_reference():
     m.integrate('discrete_time_stochastic')
     g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_vectors.npz'))
     assert np.array_equal(m.soln_array, g['strains_dts_seed1'][:31])
+
+
+def test_model_size_limits_raise_clear_errors_before_any_compilation():
+    from popdynamics_b200.basepop import BaseModel
+
+    class Wide(BaseModel):
+        def __init__(self, n):
+            BaseModel.__init__(self)
+            self.n = n
+            self.set_param('k', 0.1)
+            for i in range(n):
+                self.set_compartment('c%d' % i, 10.)
+
+        def set_flows(self):
+            for i in range(self.n):
+                self.set_fixed_transfer_rate_flow('c%d' % i, 'c%d' % ((i + 1) % self.n), 'k')
+
+    m = Wide(70)
+    m.make_times(0, 2, 1)
+    with pytest.raises(ValueError, match='at most 64 flow-table rows'):
+        m.integrate_ensemble('discrete_time_stochastic', n_members=8, output='final')
+    with pytest.raises(ValueError, match='at most 64 compartments'):
+        m.integrate_ensemble('continuous_time_stochastic', n_members=8, output='stats')
