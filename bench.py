@@ -258,7 +258,7 @@ def run_reference_arm(args):
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -795,8 +795,8 @@ def config_hybrid(g, args):
     M = args.hybrid_members
     model = configs.mix_model()
     model.device = g.local_rank
-    ensemble.integrate_hybrid(model, configs.MIX_SEGMENTS[:3], 4096, configs.MIX_CUTOFF,
-                              seed=1, device=g.local_rank)                       # warm-up / NVRTC
+    ensemble.integrate_hybrid(model, configs.MIX_SEGMENTS, 4096, configs.MIX_CUTOFF,
+                              seed=1, device=g.local_rank)       # warm-up: NVRTC of both kernels
     g.barrier()
     t0 = time.perf_counter()
     res = ensemble.integrate_hybrid(model, configs.MIX_SEGMENTS, M, configs.MIX_CUTOFF, seed=5,
@@ -917,7 +917,7 @@ def run_gpu_arm(args):
     if g.rank == 0:
         line['configs'] = configs
         line['gpu_launches'] = g.launches
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if g.world > 1:
         g.dist.destroy_process_group()
 

@@ -43,8 +43,17 @@ struct PdGilLaunch {
   (16 * PD_GIL_SLOT_BYTES <= 40960 ? 16 : 8 * PD_GIL_SLOT_BYTES <= 40960 ? 8           \
    : 4 * PD_GIL_SLOT_BYTES <= 40960 ? 4 : 2)
 #endif
+/* Large flow tables (TB: 20 rows): the cumulative interval of every row has to survive from the
+ * summation pass to the search pass -- 2 registers per row, ~100 registers per thread, two
+ * resident 256-thread blocks per SM.  With PD_GIL_CUMUL_SMEM they are parked in the thread's own
+ * column of shared memory instead (one STS.64 / LDS.64 per row and event on the idle LSU pipe,
+ * conflict-free: the bank depends on the thread only). */
+#ifndef PD_GIL_CUMUL_SMEM
+#define PD_GIL_CUMUL_SMEM (PD_LIVE_NROW > 14)
+#endif
+#define PD_GIL_WINDOW_BYTES (PD_GIL_WINDOW ? PD_GIL_SLOTS * PD_GIL_SLOT_BYTES : 0)
 extern "C" __device__ unsigned int pd_smem_bytes =
-    PD_GIL_WINDOW ? (unsigned int)(PD_GIL_SLOTS * PD_GIL_SLOT_BYTES) : 0u;
+    (unsigned int)(PD_GIL_WINDOW_BYTES + (PD_GIL_CUMUL_SMEM ? PD_NFLOW_DIM * PD_BLOCK * 8 : 0));
 
 /* the two uniforms of one reaction: exactly one Philox block when no spare is pending */
 __device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdPhilox &rng, double &u1,
@@ -60,30 +69,20 @@ __device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdInject &
 
 #define PD_GIL_WORDS ((PD_NFLOW_DIM + 31) / 32)   /* words of a flow-table row mask */
 
-/* Large flow tables (TB: 20 rows): keeping every row's rate and cumulative interval alive between
- * the summation pass and the search pass costs 4 registers per row -- 102 registers per thread,
- * two resident blocks per SM.  With PD_GIL_RECOMPUTE the search pass forms the rates and their
- * running sum again instead (the same expressions in the same order: bit-identical values) and
- * nothing per row survives the first pass. */
-#ifndef PD_GIL_RECOMPUTE
-#define PD_GIL_RECOMPUTE (PD_LIVE_NROW > 14)
-#endif
-
 /* one reaction: returns the error code (0 = ok); advances time, mutates y */
 __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const PdUniform &U,
                                                   const double (&pm)[PD_NPM_DIM],
                                                   pd_count (&y)[PD_C], double &time,
                                                   const double new_time, PdRng &rng,
                                                   pd_u64 &n_event) {
-  double yd[PD_C], mult[PD_NMULT_DIM];
-#if PD_GIL_RECOMPUTE
-  double r_one;                                 /* the row at hand only */
-#define PD_R(e) r_one
-#define PD_CUMUL_STORE(e, v)
+  double yd[PD_C], mult[PD_NMULT_DIM], r[PD_NFLOW_DIM];
+#if PD_GIL_CUMUL_SMEM
+  extern __shared__ double s_gil[];
+  double *const cumul_col = s_gil + PD_GIL_WINDOW_BYTES / 8 + threadIdx.x;   /* [row][PD_BLOCK] */
+#define PD_CUMUL(e) cumul_col[(e) * PD_BLOCK]
 #else
-  double r[PD_NFLOW_DIM], cumul[PD_NFLOW_DIM];
-#define PD_R(e) r[e]
-#define PD_CUMUL_STORE(e, v) cumul[e] = (v);
+  double cumul[PD_NFLOW_DIM];
+#define PD_CUMUL(e) cumul[e]
 #endif
 #pragma unroll
   for (int c = 0; c < PD_C; ++c) yd[c] = (double)y[c];
@@ -105,13 +104,12 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
  * (pass 2 masks with the live bits).  Python's sum() adds its first float with a plain `+` and
  * compensates from the second one on (on_float_path). */
 #define PD_ACC_INT(e)                                                                \
-  { cum += PD_R(e); PD_CUMUL_STORE(e, cum) PD_SETBIT(live, e, 1);                    \
-    if (!PD_NAIVE_SUM) f += PD_R(e); }
+  { cum += r[e]; PD_CUMUL(e) = cum; PD_SETBIT(live, e, 1); if (!PD_NAIVE_SUM) f += r[e]; }
 #define PD_ACC_FLOAT(e, live_)                                                       \
   {                                                                                  \
     const bool lv = (live_);                                                         \
-    const double rr = lv ? PD_R(e) : 0.0;                                            \
-    cum += rr; PD_CUMUL_STORE(e, cum) PD_SETBIT(live, e, lv);                        \
+    const double rr = lv ? r[e] : 0.0;                                               \
+    cum += rr; PD_CUMUL(e) = cum; PD_SETBIT(live, e, lv);                            \
     if (!PD_NAIVE_SUM) {                                                             \
       const double t = f + rr;                                                       \
       const bool big = fabs(f) >= fabs(rr);                                          \
@@ -122,9 +120,9 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
     }                                                                                \
   }
 #define PD_G1_ENTRY(e, to, is_int, rate)                                             \
-  PD_R(e) = rate; if (is_int) PD_ACC_INT(e) else PD_ACC_FLOAT(e, true)
-#define PD_G1_TRANSFER(e, from, to, rate) PD_R(e) = rate; PD_ACC_FLOAT(e, PD_R(e) > 0)
-#define PD_G1_DEATH(e, from, rate) PD_R(e) = rate; PD_ACC_FLOAT(e, PD_R(e) > 0)
+  r[e] = rate; if (is_int) PD_ACC_INT(e) else PD_ACC_FLOAT(e, true)
+#define PD_G1_TRANSFER(e, from, to, rate) r[e] = rate; PD_ACC_FLOAT(e, r[e] > 0)
+#define PD_G1_DEATH(e, from, rate) r[e] = rate; PD_ACC_FLOAT(e, r[e] > 0)
   PD_FOR_EACH_LIVE_ROW(PD_G1_ENTRY, PD_G1_TRANSFER, PD_G1_DEATH)
 #undef PD_G1_ENTRY
 #undef PD_G1_TRANSFER
@@ -158,36 +156,15 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   pd_u32 above[PD_GIL_WORDS];                   /* rows with point > cumul[e] */
 #pragma unroll
   for (int w = 0; w < PD_GIL_WORDS; ++w) above[w] = 0;
-#if PD_GIL_RECOMPUTE
-  /* the running sum again: same rates, same order, a dead row adds +0.0 as in pass 1.  The
-   * inputs are made opaque first: otherwise the compiler recognises the pass-1 expressions and
-   * keeps all their values alive across the two passes, which is what this variant avoids. */
-#pragma unroll
-  for (int c = 0; c < PD_C; ++c) asm volatile("" : "+d"(yd[c]));
-#pragma unroll
-  for (int k = 0; k < PD_NMULT; ++k) asm volatile("" : "+d"(mult[k]));
-  double cum2 = 0.0;
-#define PD_G2_ROW(e, rate)                                                           \
-  { const double r2 = rate; cum2 += ((live[(e) >> 5] >> ((e) & 31)) & 1u) ? r2 : 0.0; \
-    PD_SETBIT(above, e, point > cum2); }
-#define PD_G2_ENTRY(e, to, is_int, rate) PD_G2_ROW(e, rate)
-#define PD_G2_TRANSFER(e, from, to, rate) PD_G2_ROW(e, rate)
-#define PD_G2_DEATH(e, from, rate) PD_G2_ROW(e, rate)
-#else
-#define PD_G2_ENTRY(e, to, is_int, rate) PD_SETBIT(above, e, point > cumul[e]);
-#define PD_G2_TRANSFER(e, from, to, rate) PD_SETBIT(above, e, point > cumul[e]);
-#define PD_G2_DEATH(e, from, rate) PD_SETBIT(above, e, point > cumul[e]);
-#endif
+#define PD_G2_ENTRY(e, to, is_int, rate) PD_SETBIT(above, e, point > PD_CUMUL(e));
+#define PD_G2_TRANSFER(e, from, to, rate) PD_SETBIT(above, e, point > PD_CUMUL(e));
+#define PD_G2_DEATH(e, from, rate) PD_SETBIT(above, e, point > PD_CUMUL(e));
   PD_FOR_EACH_LIVE_ROW(PD_G2_ENTRY, PD_G2_TRANSFER, PD_G2_DEATH)
 #undef PD_G2_ENTRY
 #undef PD_G2_TRANSFER
 #undef PD_G2_DEATH
-#ifdef PD_G2_ROW
-#undef PD_G2_ROW
-#endif
 #undef PD_SETBIT
-#undef PD_R
-#undef PD_CUMUL_STORE
+#undef PD_CUMUL
   int sel = -1;
 #pragma unroll
   for (int w = 0; w < PD_GIL_WORDS; ++w) {

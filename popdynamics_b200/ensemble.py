@@ -239,6 +239,12 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
         # flow table (TB Gillespie: 20 rows, ~100 registers) are better left uncapped, and a
         # tau-leap draw list beyond two dozen rows would only spill under the cap
         min_blocks = max(1, 1024 // int(block))
+    if method == 'continuous_time_stochastic' and cm.n_flow > 16 and block == 256 and \
+            output == 'final':
+        # a large flow table keeps ~100 registers per thread alive (rates and cumulative
+        # intervals of every row): 128-thread blocks fit 4-5 of them per SM instead of 2 x 256
+        # (TB model, B200: 2.73e10 against 2.51e10 events/s, profiles/r2_tune_gillespie.txt)
+        block = 128
     kernel = _kernel_for(cm, method_code, out_code, rng_code, device, count_bits, block,
                          min_blocks,
                          (capi.FLAG_MEMBER_MASK if mask is not None else 0) |

@@ -19,8 +19,8 @@ def main():
     method = 'continuous_time_stochastic'
     cm = compiler.compile_model(model, method)
     out = torch.zeros((cm.n_comp, M), dtype=torch.float64, device='cuda')
-    for block, minb in ((256, 0), (256, 2), (256, 3), (128, 0), (128, 4), (128, 5), (128, 6),
-                        (64, 0), (64, 10)):
+    for block, minb in ((256, 0), (256, 3), (256, 4), (128, 0), (128, 5), (128, 6), (128, 8),
+                        (64, 10), (64, 16)):
         best = 1e30
         for _ in range(2):
             res = ensemble.run_compiled(model, cm, method, model.get_init_list(),
