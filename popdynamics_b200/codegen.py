@@ -37,9 +37,44 @@ def _literal(x):
 _LEAVES = ('comp', 'comp2', 'param', 'time', 'su', 'const')
 
 
+def _node_expr(g, node, name):
+    op = node[0]
+    a = name[node[1]]
+    b = name[node[2]] if node[2] >= 0 else None
+    c = name[node[3]] if node[3] >= 0 else None
+    if op in _BIN:
+        return '%s %s %s' % (a, _BIN[op], b)
+    if op == 'neg':
+        return '-%s' % a
+    if op == 'fabs':
+        return 'fabs(%s)' % a
+    if op == 'floor':
+        return 'floor(%s)' % a
+    if op == 'exp':
+        return 'exp(%s)' % a
+    if op == 'not':
+        return '!%s' % a
+    if op == 'isfinite':
+        return 'pd_isfinite(%s)' % a
+    if op == 'select':
+        return '%s ? %s : %s' % (a, b, c)
+    raise ValueError('cannot emit op %r' % (op,))
+
+
+_COSTLY = ('exp', 'div')     # what makes a select arm worth a branch
+
+
 def _emit_dag(cm, lines, roots):
-    """Straight-line evaluation of the DAG nodes ``roots`` depend on, in creation (= program)
-    order; returns node id -> C expression name."""
+    """Evaluation of the DAG nodes ``roots`` depend on, in creation (= program) order; returns
+    node id -> C expression name.
+
+    Straight-line code, with one exception: a ``select`` whose arm owns an expensive subtree (an
+    ``exp`` or a division used by nothing else) is emitted as ``if / else`` with that subtree
+    inside the branch.  These are the path joins of scale-up closures traced on time
+    (``compiler._trace_scalar_function``: `early(x) if x < 1990 else late(x)`, the `arg > 10`
+    early return of the sigmoid): their conditions depend on time only, so the lanes of a warp
+    nearly always agree and the untaken sigmoid is simply not evaluated.  Values are unchanged --
+    only unused ones are skipped.  The cheap selects of the compensated ``sum`` stay ternaries."""
     g = cm.graph
     member_slot = {k: j for j, k in enumerate(cm.member_param_slots())}
     needed, stack = set(), list(roots)
@@ -50,10 +85,52 @@ def _emit_dag(cm, lines, roots):
         needed.add(n)
         if g.nodes[n][0] not in _LEAVES:
             stack.extend(x for x in g.nodes[n][1:] if x >= 0)
-    name = {}
-    for n in cm.order:
-        if n not in needed:
+    order = [n for n in cm.order if n in needed]
+
+    def operands(n):
+        node = g.nodes[n]
+        return [] if node[0] in _LEAVES else [x for x in node[1:] if x >= 0]
+
+    users = {n: set() for n in order}
+    for n in order:
+        for x in operands(n):
+            users[x].add(n)
+    for n in roots:
+        users[n].add('root')
+
+    owner = {}                # node -> (select node, arm index) that emits it inside its branch
+    lazy = {}                 # select node -> (nodes of arm 1 in order, nodes of arm 2 in order)
+    for s_node in order:
+        node = g.nodes[s_node]
+        if node[0] != 'select' or node[2] == node[3] or node[1] in (node[2], node[3]):
             continue
+        arms = []
+        for arm in (node[2], node[3]):
+            reach, stack = set(), [arm]
+            while stack:
+                m = stack.pop()
+                if m in reach or g.nodes[m][0] in ('comp', 'comp2', 'param', 'time', 'su'):
+                    continue
+                reach.add(m)
+                stack.extend(operands(m))
+            own = set()
+            for m in sorted(reach, reverse=True):           # users before operands
+                allowed = own | ({s_node} if m == arm else set())
+                if users[m] <= allowed:
+                    own.add(m)
+            arms.append(own)
+        if arms[0] & arms[1]:
+            continue
+        if not any(g.nodes[m][0] in _COSTLY for own in arms for m in own):
+            continue
+        for k, own in enumerate(arms):
+            for m in own:
+                owner.setdefault(m, (s_node, k))            # inner selects claimed theirs first
+        lazy[s_node] = tuple(sorted(own) for own in arms)
+
+    name = {}
+
+    def emit(n, where, indent):
         node = g.nodes[n]
         op = node[0]
         if op == 'comp':
@@ -69,32 +146,25 @@ def _emit_dag(cm, lines, roots):
             name[n] = 'su[%d]' % node[1]
         elif op == 'const':
             name[n] = 'v%d' % n
-            lines.append('  const double v%d = %s;' % (n, _literal(g.const_values[n])))
-        else:
-            a = name[node[1]]
-            b = name[node[2]] if node[2] >= 0 else None
-            c = name[node[3]] if node[3] >= 0 else None
-            ctype = 'bool' if op in _BOOL_OPS else 'double'
-            if op in _BIN:
-                expr = '%s %s %s' % (a, _BIN[op], b)
-            elif op == 'neg':
-                expr = '-%s' % a
-            elif op == 'fabs':
-                expr = 'fabs(%s)' % a
-            elif op == 'floor':
-                expr = 'floor(%s)' % a
-            elif op == 'exp':
-                expr = 'exp(%s)' % a
-            elif op == 'not':
-                expr = '!%s' % a
-            elif op == 'isfinite':
-                expr = 'pd_isfinite(%s)' % a
-            elif op == 'select':
-                expr = '%s ? %s : %s' % (a, b, c)
-            else:
-                raise ValueError('cannot emit op %r' % (op,))
+            lines.append('%sconst double v%d = %s;' % (indent, n, _literal(g.const_values[n])))
+        elif n in lazy:
             name[n] = 'v%d' % n
-            lines.append('  const %s v%d = %s;' % (ctype, n, expr))
+            lines.append('%sdouble v%d;' % (indent, n))
+            for k, keyword in ((0, 'if (%s) {' % name[node[1]]), (1, '} else {')):
+                lines.append(indent + keyword)
+                for m in lazy[n][k]:
+                    if owner.get(m) == (n, k):
+                        emit(m, (n, k), indent + '  ')
+                lines.append('%s  v%d = %s;' % (indent, n, name[node[2 + k]]))
+            lines.append(indent + '}')
+        else:
+            ctype = 'bool' if op in _BOOL_OPS else 'double'
+            name[n] = 'v%d' % n
+            lines.append('%sconst %s v%d = %s;' % (indent, ctype, n, _node_expr(g, node, name)))
+
+    for n in order:
+        if n not in owner:
+            emit(n, None, '  ')
     return name
 
 

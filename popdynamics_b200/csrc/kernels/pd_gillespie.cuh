@@ -43,17 +43,8 @@ struct PdGilLaunch {
   (16 * PD_GIL_SLOT_BYTES <= 40960 ? 16 : 8 * PD_GIL_SLOT_BYTES <= 40960 ? 8           \
    : 4 * PD_GIL_SLOT_BYTES <= 40960 ? 4 : 2)
 #endif
-/* Large flow tables (TB: 20 rows): the cumulative interval of every row has to survive from the
- * summation pass to the search pass -- 2 registers per row, ~100 registers per thread, two
- * resident 256-thread blocks per SM.  With PD_GIL_CUMUL_SMEM they are parked in the thread's own
- * column of shared memory instead (one STS.64 / LDS.64 per row and event on the idle LSU pipe,
- * conflict-free: the bank depends on the thread only). */
-#ifndef PD_GIL_CUMUL_SMEM
-#define PD_GIL_CUMUL_SMEM (PD_LIVE_NROW > 14)
-#endif
-#define PD_GIL_WINDOW_BYTES (PD_GIL_WINDOW ? PD_GIL_SLOTS * PD_GIL_SLOT_BYTES : 0)
 extern "C" __device__ unsigned int pd_smem_bytes =
-    (unsigned int)(PD_GIL_WINDOW_BYTES + (PD_GIL_CUMUL_SMEM ? PD_NFLOW_DIM * PD_BLOCK * 8 : 0));
+    PD_GIL_WINDOW ? (unsigned int)(PD_GIL_SLOTS * PD_GIL_SLOT_BYTES) : 0u;
 
 /* the two uniforms of one reaction: exactly one Philox block when no spare is pending */
 __device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdPhilox &rng, double &u1,
@@ -75,15 +66,7 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
                                                   pd_count (&y)[PD_C], double &time,
                                                   const double new_time, PdRng &rng,
                                                   pd_u64 &n_event) {
-  double yd[PD_C], mult[PD_NMULT_DIM], r[PD_NFLOW_DIM];
-#if PD_GIL_CUMUL_SMEM
-  extern __shared__ double s_gil[];
-  double *const cumul_col = s_gil + PD_GIL_WINDOW_BYTES / 8 + threadIdx.x;   /* [row][PD_BLOCK] */
-#define PD_CUMUL(e) cumul_col[(e) * PD_BLOCK]
-#else
-  double cumul[PD_NFLOW_DIM];
-#define PD_CUMUL(e) cumul[e]
-#endif
+  double yd[PD_C], mult[PD_NMULT_DIM], r[PD_NFLOW_DIM], cumul[PD_NFLOW_DIM];
 #pragma unroll
   for (int c = 0; c < PD_C; ++c) yd[c] = (double)y[c];
   pd_event_mults(yd, U, pm, time, (const double *)0, mult);
@@ -104,17 +87,19 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
  * (pass 2 masks with the live bits).  Python's sum() adds its first float with a plain `+` and
  * compensates from the second one on (on_float_path). */
 #define PD_ACC_INT(e)                                                                \
-  { cum += r[e]; PD_CUMUL(e) = cum; PD_SETBIT(live, e, 1); if (!PD_NAIVE_SUM) f += r[e]; }
+  { cum += r[e]; cumul[e] = cum; PD_SETBIT(live, e, 1); if (!PD_NAIVE_SUM) f += r[e]; }
 #define PD_ACC_FLOAT(e, live_)                                                       \
   {                                                                                  \
     const bool lv = (live_);                                                         \
     const double rr = lv ? r[e] : 0.0;                                               \
-    cum += rr; PD_CUMUL(e) = cum; PD_SETBIT(live, e, lv);                            \
+    cum += rr; cumul[e] = cum; PD_SETBIT(live, e, lv);                            \
     if (!PD_NAIVE_SUM) {                                                             \
+      /* CPython's correction term (hi - t) + lo, hi the larger magnitude, IS the rounding  \
+       * error of f + rr, which is exactly representable; Knuth's branch-free TwoSum yields  \
+       * the same number without the compare and four selects */                           \
       const double t = f + rr;                                                       \
-      const bool big = fabs(f) >= fabs(rr);                                          \
-      const double hi = big ? f : rr, lo = big ? rr : f;                             \
-      const double ci = (hi - t) + lo;                                               \
+      const double bb = t - f;                                                       \
+      const double ci = (f - (t - bb)) + (rr - bb);                                  \
       comp += on_float_path ? ci : 0.0;                                              \
       f = t; on_float_path |= lv;                                                    \
     }                                                                                \
@@ -156,15 +141,14 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   pd_u32 above[PD_GIL_WORDS];                   /* rows with point > cumul[e] */
 #pragma unroll
   for (int w = 0; w < PD_GIL_WORDS; ++w) above[w] = 0;
-#define PD_G2_ENTRY(e, to, is_int, rate) PD_SETBIT(above, e, point > PD_CUMUL(e));
-#define PD_G2_TRANSFER(e, from, to, rate) PD_SETBIT(above, e, point > PD_CUMUL(e));
-#define PD_G2_DEATH(e, from, rate) PD_SETBIT(above, e, point > PD_CUMUL(e));
+#define PD_G2_ENTRY(e, to, is_int, rate) PD_SETBIT(above, e, point > cumul[e]);
+#define PD_G2_TRANSFER(e, from, to, rate) PD_SETBIT(above, e, point > cumul[e]);
+#define PD_G2_DEATH(e, from, rate) PD_SETBIT(above, e, point > cumul[e]);
   PD_FOR_EACH_LIVE_ROW(PD_G2_ENTRY, PD_G2_TRANSFER, PD_G2_DEATH)
 #undef PD_G2_ENTRY
 #undef PD_G2_TRANSFER
 #undef PD_G2_DEATH
 #undef PD_SETBIT
-#undef PD_CUMUL
   int sel = -1;
 #pragma unroll
   for (int w = 0; w < PD_GIL_WORDS; ++w) {

@@ -242,9 +242,11 @@ def run_compiled(model, cm, method, y, target_times, n_members, output='full', s
     if method == 'continuous_time_stochastic' and cm.n_flow > 16 and block == 256 and \
             output == 'final':
         # a large flow table keeps ~100 registers per thread alive (rates and cumulative
-        # intervals of every row): 128-thread blocks fit 4-5 of them per SM instead of 2 x 256
-        # (TB model, B200: 2.73e10 against 2.51e10 events/s, profiles/r2_tune_gillespie.txt)
+        # intervals of every row): five 128-thread blocks at 94 registers fit an SM instead of
+        # two of 256 (TB model, B200: 2.84e10 against 2.51e10 events/s,
+        # profiles/r2_tune_gillespie.txt)
         block = 128
+        min_blocks = min_blocks or 5
     kernel = _kernel_for(cm, method_code, out_code, rng_code, device, count_bits, block,
                          min_blocks,
                          (capi.FLAG_MEMBER_MASK if mask is not None else 0) |
