@@ -91,12 +91,15 @@ class Sym(object):
     ``old_div`` and the path Python's ``sum`` takes, the value itself is always carried in fp64
     (exact below 2**53)."""
 
-    __slots__ = ('g', 'n', 'is_int', 'is_bool')
+    __slots__ = ('g', 'n', 'is_int', 'is_bool', 'first_int')
     __array_ufunc__ = None      # numpy scalars defer to our reflected operators
     __hash__ = None
 
-    def __init__(self, g, n, is_int=False, is_bool=False):
+    def __init__(self, g, n, is_int=False, is_bool=False, first_int=False):
         self.g, self.n, self.is_int, self.is_bool = g, n, is_int, is_bool
+        # an ODE compartment whose INITIAL value is a Python int: the reference's first
+        # derivative call sees that int, every later one a float (basepop.py:683-684)
+        self.first_int = first_int
 
     # -- coercion ---------------------------------------------------------------------------
     def _lift(self, other):
@@ -121,7 +124,9 @@ class Sym(object):
         if a.is_bool or b.is_bool:
             raise TraceError('arithmetic on a traced comparison result is not supported')
         as_int = a.is_int and b.is_int and op != 'div'
-        return Sym(self.g, self.g.add(op, a.n, b.n), is_int=as_int)
+        return Sym(self.g, self.g.add(op, a.n, b.n), is_int=as_int,
+                   first_int=(a.is_int or a.first_int) and (b.is_int or b.first_int)
+                   and not as_int and op != 'div')
 
     def __add__(self, o): return self._bin('add', o)
     def __radd__(self, o): return self._bin('add', o, True)
@@ -203,7 +208,18 @@ class Sym(object):
         return 'Sym(#%d%s)' % (self.n, ',int' if self.is_int else '')
 
 
+def _first_step_hazard(a, b):
+    """old_div / // of two values that are ints on the FIRST derivative call only (initial
+    compartments given as Python ints): the reference floors there and divides truly on every
+    later sub-step; one compiled expression cannot be both."""
+    if (a.first_int or b.first_int) and (a.is_int or a.first_int) and (b.is_int or b.first_int):
+        raise TraceError(
+            'old_div / // meets a compartment whose initial value is a Python int: the reference '
+            'would floor on the first sub-step only; give the initial value as a float')
+
+
 def _floordiv(a, b):
+    _first_step_hazard(a, b)
     if not (a.is_int and b.is_int):
         raise TraceError('// is only lowered for two integer operands')
     q = a.g.add('div', a.n, b.n)
@@ -216,6 +232,7 @@ def sym_old_div(a, b):
     a, b = sym._lift(a), sym._lift(b)
     if a is None or b is None:
         raise TraceError('old_div operand cannot be traced')
+    _first_step_hazard(a, b)
     if a.is_int and b.is_int:
         return _floordiv(a, b)
     return a / b
@@ -542,7 +559,11 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
     cm.graph = g
     index_of = {label: i for i, label in enumerate(cm.labels)}
 
-    comps = {label: Sym(g, g.add('comp', i), is_int=integer_state)
+    first_int = {label: (not integer_state and not diagnostics and not is_continue and
+                         method in ('explicit',) and
+                         _is_intlike(model.init_compartments.get(label)))
+                 for label in cm.labels}
+    comps = {label: Sym(g, g.add('comp', i), is_int=integer_state, first_int=first_int[label])
              for i, label in enumerate(cm.labels)}
     time_sym = Sym(g, g.add('time'))
 

@@ -217,3 +217,21 @@ def test_nvrtc_errors_surface_with_the_log(built_library):
     cm = helpers.compiled(helpers.make_model('sir'), 'explicit')
     with pytest.raises(capi.PopdynError, match='stochastic'):
         capi.Model(cm.cuda_source(), capi.EXPLICIT, capi.STATS, 0, 0, 3, 2, 0, 0, 2)
+
+
+def test_old_div_on_an_int_initial_compartment_is_rejected_for_the_ode_method():
+    # the reference's first derivative call sees the Python ints of set_compartment and floors
+    # old_div(int, int) there, then divides truly: one compiled expression cannot do both
+    class Halving(_Weird):
+        def __init__(self, init):
+            _Weird.__init__(self, lambda s: old_div(s.compartments['a'], 4) * s.params['k'])
+            self.set_compartment('a', init)
+
+    from popdynamics_b200.basepop import old_div
+    with pytest.raises(TraceError, match='first sub-step'):
+        helpers.compiled(Halving(10), 'explicit')
+    helpers.compiled(Halving(10.), 'explicit')                   # floats: true division
+    cm = helpers.compiled(Halving(10), 'discrete_time_stochastic')  # integer state: floors always
+    assert 'floor(' in cm.cuda_source()
+    # the shipped examples give int initial values but never divide them
+    helpers.compiled(helpers.make_model('strains'), 'explicit')
