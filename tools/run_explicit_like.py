@@ -19,12 +19,17 @@ def main():
     rows = ensemble._member_param_rows(cm, M)
     mp = torch.stack([torch.from_numpy(r) for r in rows]).cuda()
     out = torch.empty((cm.n_comp, M), dtype=torch.float64, device='cuda')
+    block = int(os.environ.get('PD_RUN_BLOCK', 256))
+    minb = int(os.environ.get('PD_RUN_MIN_BLOCKS', 0))
     for _ in range(2):
         res = ensemble.run_compiled(model, cm, method, model.get_init_list(), model.target_times,
-                                    M, output='final', device=0, member_params=mp, out=out)
+                                    M, output='final', device=0, member_params=mp, out=out,
+                                    block=block, min_blocks=minb)
     steps = int(res.info['n_steps'])
-    print('%s %s M=%d regs=%d  %.2f ms  %.3e steps/s' % (method, config, M,
-          res.info['regs_per_thread'], res.info['kernel_ms'], steps / (res.info['kernel_ms'] * 1e-3)))
+    print('%s %s M=%d block=%d minb=%d regs=%d blocks/sm=%d  %.2f ms  %.3e steps/s'
+          % (method, config, M, block, minb, res.info['regs_per_thread'],
+             res.info['blocks_per_sm'], res.info['kernel_ms'],
+             steps / (res.info['kernel_ms'] * 1e-3)))
 
 
 if __name__ == '__main__':
