@@ -787,6 +787,18 @@ def config_tb(g, args):
     }
 
 
+def hybrid_reference_baseline():
+    """The reference's own mix_model loop (oracle/_ref) on the host cores; None when it did not
+    ship with this run."""
+    try:
+        from oracle import ref_runner
+        if ref_runner.available():
+            return ref_runner.time_mix_hybrid(3.0, host_threads())
+    except Exception as exc:                                   # pragma: no cover
+        return {'unavailable': str(exc)}
+    return None
+
+
 def config_hybrid(g, args):
     """Config 5b: mix_model.py's day-by-day switching between Gillespie and explicit Euler."""
     from examples import configs
@@ -830,6 +842,7 @@ def config_hybrid(g, args):
         'e2e': {'value': g.world * M / wall, 'unit': 'members/s', 'h2d_bytes_per_step': 24,
                 'd2h_bytes_per_step': 0, 'seconds': wall},
         'roofline': None,
+        'cpu_baseline': hybrid_reference_baseline(),
         'parity': {'what': 'closed population never grows and no compartment is negative; share of '
                            '(member, segment) pairs integrated explicitly %.3f; per-member '
                            'bit-exact comparison with the oracle loop is in '
@@ -890,7 +903,9 @@ def config_adaptive(g, args):
                      'traffic': None,
                      'per_unit': '%.0f fp64 operations per attempted step (7 derivative '
                                  'evaluations + stage combinations + error norm)' % ops},
-        'cpu_baseline': None,
+        'cpu_baseline': {'unavailable': 'the reference\'s integrate(\'scipy\') aborts with '
+                                        'AssertionError on this model beyond ~300 days (its '
+                                        'checks() fires inside LSODA, oracle/make_golden.py)'},
         'parity': {'what': 'member 0 over 300 days vs the unmodified reference\'s '
                            'integrate(\'scipy\') (odeint / LSODA) trajectory: max difference '
                            '%.2e of the largest compartment (tolerance 2e-6, DESIGN.md); members '

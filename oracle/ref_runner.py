@@ -83,20 +83,65 @@ def _worker(seconds, seed):
     return {'members': m1, 'seconds': e1, 'whole_members': m2, 'whole_seconds': e2}
 
 
-def time_strains_dts(seconds, n_proc):
-    """Aggregate comp-steps/s of ``n_proc`` worker processes, >= ``seconds`` each."""
+def _hybrid_worker(seconds, seed):
+    """The day-by-day switching loop of examples/mix_model.py:107-136 (a script-level function
+    there, restated here around the reference's own SirModel and integrate())."""
+    import random
+    import numpy
+    Sir = example_classes('mix_model')['SirModel']
+    random.seed(seed)
+    numpy.random.seed(seed)
+    members, t0 = 0, time.perf_counter()
+    while True:
+        model = Sir({'start_population': 100})
+        model.calculate_diagnostics = lambda: None
+        day, final, cutoff, dt = 1, 50, 3, 0.2
+        model.make_times(0, day, dt)
+        model.integrate(method='continuous_time_stochastic')
+        while day < final:
+            start, day = day, min(final, day + 1)
+            method = 'explicit' if min(model.compartments.values()) > cutoff \
+                else 'continuous_time_stochastic'
+            model.make_times(start, day, dt)
+            model.integrate(method=method, is_continue=True)
+        members += 1
+        elapsed = time.perf_counter() - t0
+        if elapsed >= seconds:
+            return {'members': members, 'seconds': elapsed}
+
+
+def _run_workers(flag, seconds, n_proc):
     env = dict(os.environ, OMP_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1', MKL_NUM_THREADS='1')
     env['PYTHONPATH'] = os.path.dirname(HERE) + os.pathsep + env.get('PYTHONPATH', '')
-    procs = [subprocess.Popen([sys.executable, '-m', 'oracle.ref_runner', '--worker',
-                               str(seconds), str(1000 + k)], stdout=subprocess.PIPE, env=env,
+    procs = [subprocess.Popen([sys.executable, '-m', 'oracle.ref_runner', flag, str(seconds),
+                               str(1000 + k)], stdout=subprocess.PIPE, env=env,
                               cwd=os.path.dirname(HERE), text=True) for k in range(n_proc)]
-    rate = whole = 0.0
-    members = 0
+    results = []
     for p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError('reference worker failed')
-        r = json.loads(out.strip().splitlines()[-1])
+        results.append(json.loads(out.strip().splitlines()[-1]))
+    return results
+
+
+def time_mix_hybrid(seconds, n_proc):
+    """Members per second of the reference's mix_model hybrid loop on ``n_proc`` host cores."""
+    results = _run_workers('--hybrid-worker', seconds, n_proc)
+    rate = sum(r['members'] / r['seconds'] for r in results)
+    members = sum(r['members'] for r in results)
+    return {'value': rate, 'unit': 'members/s', 'cores': n_proc, 'kind': 'reference',
+            'sample': '%d members x 50 one-day segments in %d worker processes (>= %.1f s each); '
+                      'unmodified reference integrate() from oracle/_ref driven by the loop of '
+                      'examples/mix_model.py:107-136, diagnostics stubbed'
+                      % (members, n_proc, seconds)}
+
+
+def time_strains_dts(seconds, n_proc):
+    """Aggregate comp-steps/s of ``n_proc`` worker processes, >= ``seconds`` each."""
+    rate = whole = 0.0
+    members = 0
+    for r in _run_workers('--worker', seconds, n_proc):
         rate += r['members'] * 1000 * 5 / r['seconds']
         whole += r['whole_members'] * 1000 * 5 / r['whole_seconds']
         members += r['members']
@@ -113,5 +158,7 @@ def time_strains_dts(seconds, n_proc):
 if __name__ == '__main__':
     if len(sys.argv) >= 4 and sys.argv[1] == '--worker':
         print(json.dumps(_worker(float(sys.argv[2]), int(sys.argv[3]))))
+    elif len(sys.argv) >= 4 and sys.argv[1] == '--hybrid-worker':
+        print(json.dumps(_hybrid_worker(float(sys.argv[2]), int(sys.argv[3]))))
     else:
         print(json.dumps(time_strains_dts(2.0, len(os.sched_getaffinity(0))), indent=1))
