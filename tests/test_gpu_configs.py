@@ -264,3 +264,38 @@ def test_two_gpus_over_nccl_equal_one_gpu():
     assert np.array_equal(q, one.quantiles([0.25, 0.5, 0.975]))
     assert np.array_equal(mean, one.mean())
     assert all(r is not None and 'member 3999' in r for r in raised), raised
+
+
+def test_chunked_pipeline_with_per_member_initial_states_and_a_member_mask(monkeypatch):
+    # y0 [C][M] from host arrays, FULL stochastic output, and a host mask, all through the chunks
+    n = 3000
+    rng = np.random.default_rng(11)
+    def build():
+        m = helpers.make_model('strains')
+        m.set_compartment('susceptible', np.floor(rng.uniform(800., 1200., n)))
+        m.set_compartment('infectious_invader', np.floor(rng.uniform(1., 5., n)))
+        m.make_times(0, 25, 1)
+        return m
+    rng = np.random.default_rng(11)
+    whole = build().integrate_ensemble('continuous_time_stochastic', n_members=n, output='full',
+                                       seed=2, member_offset=50)
+    monkeypatch.setenv('POPDYN_CHUNK_MEMBERS', '700')
+    rng = np.random.default_rng(11)
+    parts = build().integrate_ensemble('continuous_time_stochastic', n_members=n, output='full',
+                                       seed=2, member_offset=50)
+    assert parts.info['n_launch'] == 5 and np.array_equal(parts.soln, whole.soln)
+    assert int(parts.info['n_steps']) == int(whole.info['n_steps'])
+    # masked explicit launch over host buffers: untouched members keep what the buffer held
+    rng = np.random.default_rng(11)
+    m = build()
+    mask = (np.arange(n) % 3 == 0).astype(np.uint8)
+    out = np.full((5, n), -7.0)
+    cm = helpers.compiled(m, 'explicit')
+    res = ensemble.run_compiled(m, cm, 'explicit', m.get_init_list(), m.target_times, n,
+                                output='final', out=out, mask=mask, mask_value=1)
+    assert res.info['n_launch'] == 5
+    assert np.all(out[:, mask == 0] == -7.0) and np.all(out[:, mask == 1] >= 0.0)
+    monkeypatch.delenv('POPDYN_CHUNK_MEMBERS')
+    rng = np.random.default_rng(11)
+    ref = build().integrate_ensemble('explicit', n_members=n, output='final')
+    assert np.array_equal(out[:, mask == 1], ref.final[:, mask == 1])
