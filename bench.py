@@ -613,26 +613,23 @@ def explicit_sweep_config(g, args, name, model_fn, total_members, ops_key, want_
     torch.cuda.empty_cache()
 
     # end to end: host parameter columns in (chunked, double-buffered inside the C-ABI), host
-    # result out -- the final state, or one diagnostic var per member
+    # result out -- the final state, or one diagnostic var per member written by the integrator
+    # kernel itself (final_vars: the diagnostics pass of the final state fused into it)
     def e2e_step():
-        r = model.integrate_ensemble('explicit', n_members=M, output='final',
-                                     device=g.local_rank,
-                                     out=(torch.empty((C, M), dtype=torch.float64, device=g.dev)
-                                          if want_var else None))
-        moved = [r.info['h2d_bytes'], r.info['d2h_bytes']]
         if want_var:
-            host = np.empty((1, M), dtype=np.float64)
-            d = ensemble.diagnostics(model, r, want_vars=[want_var], out=host)
-            moved[0] += d.info['h2d_bytes']
-            moved[1] += d.info['d2h_bytes']
-            return r, host[0], moved, r.info['n_launch']
-        return r, r.final, moved, r.info['n_launch']
+            r = model.integrate_ensemble('explicit', n_members=M, final_vars=[want_var],
+                                         device=g.local_rank)
+            return r, r.final_var(want_var), [r.info['h2d_bytes'], r.info['d2h_bytes']], \
+                r.info['n_launch']
+        r = model.integrate_ensemble('explicit', n_members=M, output='final',
+                                     device=g.local_rank)
+        return r, r.final, [r.info['h2d_bytes'], r.info['d2h_bytes']], r.info['n_launch']
     g.barrier()
     t0 = time.perf_counter()
     r, host_out, moved, n_chunk = e2e_step()
     g.barrier()
     e2e_s = g.max_over_ranks(time.perf_counter() - t0)
-    g.launches += n_chunk + (1 if want_var else 0)
+    g.launches += n_chunk
     parity = check(s0, s1, r, host_out) if g.rank == 0 else None
     del r
     torch.cuda.empty_cache()

@@ -53,7 +53,11 @@ enum { PD_EXPLICIT = 0,   /* integrate_explicit,                      basepop.py
 /* output selector */
 enum { PD_FULL = 0,       /* soln [T][C][M] fp64 (the reference's soln_array per member)      */
        PD_FINAL = 1,      /* final state [C][M] fp64                                          */
-       PD_STATS = 2 };    /* streaming ensemble moments + histograms (stochastic only)        */
+       PD_STATS = 2,      /* streaming ensemble moments + histograms (stochastic only)        */
+       PD_FINAL_VARS = 3 };/* ODE integrators: the diagnostics pass (basepop.py:927-948) of the
+                             FINAL state fused into the kernel -- final_state receives
+                             [n_final_var][M] vars (e.g. model.vars['proportion'],
+                             examples/rmit_tb_model.py:143) instead of the compartments       */
 /* uniform source for the stochastic integrators */
 enum { PD_PHILOX = 0,     /* native counter-based Philox4x32-10                               */
        PD_INJECT = 1 };   /* caller-supplied uniform stream replacing random.random (:174,
@@ -143,8 +147,11 @@ typedef struct {
   double *final_state;            /* PD_FINAL [C][M]                                          */
   void *stream;
   const uint8_t *mask;            /* as in pd_stoch_run                                       */
-  int32_t mask_value, reserved;
+  int32_t mask_value;
+  int32_t n_final_var;            /* PD_FINAL_VARS: rows of final_state (PD_NFVAR of the header) */
   const double *const *member_param_rows; /* as in pd_stoch_run                                */
+  double t_final;                 /* PD_FINAL_VARS: self.time of the diagnostics pass, i.e. the
+                                     last target time                                         */
 } pd_explicit_run;
 
 /* The diagnostics pass over stored trajectories (model built with method PD_DIAGNOSTICS, the
@@ -178,8 +185,9 @@ typedef struct {
   double first_step;              /* 0: estimated per member                                  */
   int64_t max_steps;              /* attempted-step budget per member (PD_ERR_MAX_STEPS)      */
   double *soln;                   /* PD_FULL  [T][C][M]                                       */
-  double *final_state;            /* PD_FINAL [C][M]                                          */
+  double *final_state;            /* PD_FINAL [C][M], PD_FINAL_VARS [n_final_var][M]          */
   void *stream;
+  int32_t n_final_var, reserved;
 } pd_adaptive_run;
 
 /* ---- library ---------------------------------------------------------------------------- */

@@ -17,11 +17,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libpopdyn_b200.so')
 
 EXPLICIT, TAU_LEAP, GILLESPIE, DIAGNOSTICS, ADAPTIVE = 0, 1, 2, 3, 4
-FULL, FINAL, STATS = 0, 1, 2
+FULL, FINAL, STATS, FINAL_VARS = 0, 1, 2, 3
 PHILOX, INJECT = 0, 1
 METHOD_CODES = {'explicit': EXPLICIT, 'discrete_time_stochastic': TAU_LEAP,
                 'continuous_time_stochastic': GILLESPIE, 'scipy': ADAPTIVE}
-OUTPUT_CODES = {'full': FULL, 'final': FINAL, 'stats': STATS}
+OUTPUT_CODES = {'full': FULL, 'final': FINAL, 'stats': STATS, 'final_vars': FINAL_VARS}
 
 PD_E_NO_DEVICE, PD_E_MODEL = -4, -5
 DEVICE_ERRORS = {
@@ -96,8 +96,8 @@ class ExplicitRun(C.Structure):
                 ('n_sub', C.c_void_p), ('dt', C.c_void_p), ('t_eval', C.c_void_p),
                 ('scaleup_table', C.c_void_p), ('n_steps', C.c_int64),
                 ('soln', C.c_void_p), ('final_state', C.c_void_p), ('stream', C.c_void_p),
-                ('mask', C.c_void_p), ('mask_value', C.c_int32), ('reserved', C.c_int32),
-                ('member_param_rows', C.c_void_p)]
+                ('mask', C.c_void_p), ('mask_value', C.c_int32), ('n_final_var', C.c_int32),
+                ('member_param_rows', C.c_void_p), ('t_final', C.c_double)]
 
 
 class DiagRun(C.Structure):
@@ -116,7 +116,7 @@ class AdaptiveRun(C.Structure):
                 ('member_param_rows', C.c_void_p), ('target_times', C.c_void_p),
                 ('rtol', C.c_double), ('atol', C.c_double), ('first_step', C.c_double),
                 ('max_steps', C.c_int64), ('soln', C.c_void_p), ('final_state', C.c_void_p),
-                ('stream', C.c_void_p)]
+                ('stream', C.c_void_p), ('n_final_var', C.c_int32), ('reserved', C.c_int32)]
 
 
 _lib = None

@@ -370,6 +370,20 @@ def emit_model_header(cm):
         w('}')
         w('')
 
+    # ---- diagnostics vars of the FINAL state, written by the ODE kernels in PD_OUT_FINAL_VARS ---
+    w('#define PD_NFVAR %d' % len(cm.final_var_nodes))
+    w('#define PD_NFVAR_DIM %d' % max(len(cm.final_var_nodes), 1))
+    if cm.final_var_nodes:
+        w('__device__ __forceinline__ void pd_final_vars' + _SIGNATURE +
+          'double (&out)[PD_NFVAR_DIM]) {')
+        body = []
+        name = _emit_dag(cm, body, list(cm.final_var_nodes))
+        for k, n in enumerate(cm.final_var_nodes):
+            body.append('  out[%d] = %s;  // %s' % (k, name[n], cm.final_var_labels[k]))
+        out.extend(body)
+        w('}')
+        w('')
+
     # ---- per-step multipliers of the stochastic integrators ------------------------------
     w('__device__ __forceinline__ bool pd_event_mults' + _SIGNATURE +
       'double (&mult)[PD_NMULT_DIM]) {')

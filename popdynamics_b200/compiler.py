@@ -27,6 +27,7 @@ import hashlib
 import math
 import numbers
 import sys
+import threading
 
 import numpy
 
@@ -443,6 +444,8 @@ class CompiledModel(object):
         self.diag_labels = []      # var_labels of the diagnostics pass, in the reference's order
         self.diag_nodes = []       # node of every diagnostic var
         self.diag_flow_nodes = []  # net flow of every compartment (flow_array)
+        self.final_var_labels = [] # diagnostics vars of the final state, fused into the integrator
+        self.final_var_nodes = []
 
     # ---- sizes
     @property
@@ -518,8 +521,20 @@ class _Tracer(object):
         return self.param_symbol('<%s>' % tag, value)
 
 
+# Tracing shadows builtins.sum and math.exp process-wide while a hook runs: one trace at a time.
+_TRACE_LOCK = threading.RLock()
+
+
 def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=False,
-                  want_vars=None):
+                  want_vars=None, final_vars=None):
+    """Thread-safe front door of ``_compile_model`` (see there)."""
+    with _TRACE_LOCK:
+        return _compile_model(model, method, is_continue, naive_sum, diagnostics, want_vars,
+                              final_vars)
+
+
+def _compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=False,
+                   want_vars=None, final_vars=None):
     """Lower ``model`` for ``method`` ('explicit', 'discrete_time_stochastic',
     'continuous_time_stochastic', 'scipy').  ``model.set_flows()`` must already have run
     (``check_flow_transfers``, basepop.py:638-656).
@@ -536,7 +551,13 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
     ``calculate_diagnostic_vars`` hook run; every numeric entry of ``self.vars`` is an output
     (``var_array``) and so is the net flow of every compartment (``flow_array``).  ``want_vars``
     (a list of var labels) keeps only those outputs, in the reference's order: everything that
-    feeds none of them is eliminated from the device code."""
+    feeds none of them is eliminated from the device code.
+
+    ``final_vars`` (ODE methods only) fuses the diagnostics pass of the FINAL state into the
+    integrator: the same hooks are traced a second time on the final compartments the way
+    ``calculate_diagnostics`` runs them (plain ``sum`` fold, vars not cleared) and the kernel
+    writes those vars instead of the state -- one scalar per member for a calibration sweep that
+    reads ``model.vars['proportion']`` (examples/rmit_tb_model.py:143)."""
     from .basepop import BaseModel
 
     integer_state = method not in ('explicit', 'scipy') and not diagnostics
@@ -617,6 +638,9 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
     else:
         bg_sym = tr.anonymous_param(bg, 'background_death')
 
+    initial_vars = dict(traced_vars)
+    if final_vars and (integer_state or diagnostics):
+        raise ValueError("final_vars is defined for the ODE methods ('explicit', 'scipy')")
     saved = dict(params=model.params, compartments=model.compartments, vars=model.vars,
                  time=model.time, fixed=model.fixed_transfer_rate_flows,
                  inf=model.infection_death_rate_flows, bg=model.background_death_rate,
@@ -734,6 +758,21 @@ def compile_model(model, method, is_continue=False, naive_sum=None, diagnostics=
                     raise KeyError('the diagnostics pass defines no var(s) %s' % missing)
             cm.diag_flow_nodes = [as_sym(model.flows[label], 'flows[%r]' % label).n
                                   for label in cm.labels]
+        if final_vars:
+            # calculate_diagnostics on the final state (basepop.py:927-948): compartments are the
+            # numpy.float64 of soln_array (plain sum fold), vars still hold the scale-up values
+            # of the last derivative call, then the three hooks run
+            model.vars = dict(initial_vars)
+            model.flows = {}
+            with _patched_sum(True):
+                model.calculate_vars()
+                model.calculate_flows()
+                model.calculate_diagnostic_vars()
+            for label in final_vars:
+                if label not in model.vars:
+                    raise KeyError('the diagnostics pass defines no var %r' % (label,))
+                cm.final_var_labels.append(label)
+                cm.final_var_nodes.append(as_sym(model.vars[label], 'vars[%r]' % label).n)
     finally:
         model.params = saved['params']
         model.compartments = saved['compartments']
@@ -776,7 +815,7 @@ def live_order(cm):
     topological."""
     g = cm.graph
     roots = list(cm.flow_node) + list(cm.check_nodes) + list(cm.post_check_nodes) + \
-        list(cm.diag_nodes) + list(cm.diag_flow_nodes)
+        list(cm.diag_nodes) + list(cm.diag_flow_nodes) + list(cm.final_var_nodes)
     live = set()
     stack = list(roots)
     while stack:

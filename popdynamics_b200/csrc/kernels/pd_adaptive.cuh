@@ -162,6 +162,14 @@ pd_adaptive_kernel(const __grid_constant__ PdAdaptiveLaunch L) {
 #pragma unroll
   for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * a.out_ld + m] = y[c];
 #endif
+#if PD_OUT_MODE == PD_OUT_FINAL_VARS
+  {
+    double fv[PD_NFVAR_DIM];
+    pd_final_vars(y, L.U, pm, a.target[a.n_time - 1], su, fv);
+#pragma unroll
+    for (int v = 0; v < PD_NFVAR; ++v) a.final_state[(size_t)v * a.out_ld + m] = fv[v];
+  }
+#endif
   if (bad) pd_raise(a.err, bad, a.member0 + m, bad_at);
   if (a.n_steps) {
     /* a full warp that arrives together adds up its counts through lane 0 */

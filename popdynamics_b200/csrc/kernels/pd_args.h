@@ -10,6 +10,7 @@
 #define PD_OUT_FULL 0   /* soln  [T][C][M] fp64, member fastest (coalesced stores)              */
 #define PD_OUT_FINAL 1  /* final [C][M] fp64                                                     */
 #define PD_OUT_STATS 2  /* streaming moments u64 [T][C][2] + histograms u32 [rows][C][bins]      */
+#define PD_OUT_FINAL_VARS 3 /* ODE kernels: diagnostics vars of the final state [PD_NFVAR][M]    */
 
 #define PD_RNG_PHILOX 0 /* Philox4x32-10, key = seed, counter = (draw block, global member id)   */
 #define PD_RNG_INJECT 1 /* uniforms[n_uniform][M] fp64 consumed in order (parity tests)          */
@@ -106,6 +107,8 @@ typedef struct {
   long long member0;           /* global id of member 0 of this launch (error reports)           */
   long long pm_ld;             /* row stride (elements) of pm                                    */
   long long out_ld;            /* row stride of soln / final_state                               */
+  double t_final;              /* last target time (PD_OUT_FINAL_VARS: time of the diagnostics)  */
+  long long n_steps;           /* sub-steps in total (PD_OUT_FINAL_VARS: last scale-up row)      */
 } PdExplicitArgs;
 
 typedef struct {

@@ -77,5 +77,20 @@ pd_explicit_kernel(const __grid_constant__ PdExplicitLaunch L) {
 #pragma unroll
   for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * a.out_ld + m] = y[c];
 #endif
+#if PD_OUT_MODE == PD_OUT_FINAL_VARS
+  {
+    /* calculate_diagnostics of the final state (:927-948), fused: scale-up vars keep the values
+     * of the last derivative call (the reference never re-evaluates them in that pass) */
+#if PD_NSU > 0
+    const double *su_last = a.su_table + (a.n_steps > 0 ? a.n_steps - 1 : 0) * PD_NSU;
+#else
+    const double *su_last = (const double *)0;
+#endif
+    double fv[PD_NFVAR_DIM];
+    pd_final_vars(y, L.U, pm, a.t_final, su_last, fv);
+#pragma unroll
+    for (int v = 0; v < PD_NFVAR; ++v) a.final_state[(size_t)v * a.out_ld + m] = fv[v];
+  }
+#endif
   if (!ok) pd_raise(a.err, PD_ERR_CHECKS, a.member0 + m, bad_at);
 }

@@ -299,3 +299,85 @@ def test_chunked_pipeline_with_per_member_initial_states_and_a_member_mask(monke
     rng = np.random.default_rng(11)
     ref = build().integrate_ensemble('explicit', n_members=n, output='final')
     assert np.array_equal(out[:, mask == 1], ref.final[:, mask == 1])
+
+
+def test_two_threads_share_one_kernel_handle_without_sharing_an_error_flag():
+    # the error block, events and staging scratch belong to a per-run slot: concurrent runs of the
+    # same cached handle (ctypes releases the GIL) must neither lose nor misattribute a failure
+    import threading
+    from examples import models
+    n = 4096
+    bad = dict(rho=0.4675096681435942, sigma1=0.4864215594357471, sigma2=0.40346161064467484,
+               sigma3=0.40408850758699627, beta=462.931574029995)
+
+    def build(fail):
+        p = dict(helpers.RMIT)
+        for key, value in bad.items():
+            column = np.full(n, 50. if key == 'beta' else helpers.RMIT.get(key, 0.))
+            if fail:
+                column[n // 2] = value
+            p[key] = column
+        m = models.RmitTbModel(p)
+        m.make_times(0, 500., 1.)
+        return m
+
+    good, failing = build(False), build(True)
+    want = good.integrate_ensemble('explicit', n_members=n, output='final').final
+    outcomes = {'good': [], 'failing': []}
+
+    def work(name, model):
+        for _ in range(6):
+            res = model.integrate_ensemble('explicit', n_members=n, output='final', check=False)
+            outcomes[name].append((res.info['err_code'], res.info['err_member'],
+                                   np.array_equal(res.final, want) if name == 'good' else True))
+
+    threads = [threading.Thread(target=work, args=('good', good)),
+               threading.Thread(target=work, args=('failing', failing))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert outcomes['good'] == [(0, 0, True)] * 6
+    assert [o[:2] for o in outcomes['failing']] == [(1, n // 2)] * 6
+
+
+def test_final_vars_fused_into_the_ode_kernels_equal_the_diagnostics_pass(golden):
+    # config 5's output: model.vars['proportion'] of the final state, straight from the kernel
+    n = 6000
+    model = configs.rmit_sweep(0, n)
+    fused = model.integrate_ensemble('explicit', n_members=n, final_vars=['proportion'])
+    assert fused.output == 'final_vars' and fused.final_vars.shape == (1, n)
+    assert np.array_equal(fused.final_var('proportion')[:6], golden['rmit_fig2_proportion'])
+    state = model.integrate_ensemble('explicit', n_members=n, output='final')
+    two_pass = ensemble.diagnostics(model, state, want_vars=['proportion'])
+    assert np.array_equal(fused.final_vars, two_pass.vars)
+    # several vars, the SEIR-demography sweep, through the chunk pipeline
+    seir = configs.seir_sweep(0, 3000)
+    seir.make_times(0, 400, 1)
+    import os
+    os.environ['POPDYN_CHUNK_MEMBERS'] = '1024'
+    try:
+        fused = seir.integrate_ensemble('explicit', n_members=3000,
+                                        final_vars=['prevalence', 'population', 'incidence'])
+    finally:
+        del os.environ['POPDYN_CHUNK_MEMBERS']
+    assert fused.info['n_launch'] == 3
+    state = seir.integrate_ensemble('explicit', n_members=3000, output='final')
+    every = ensemble.diagnostics(seir, state)
+    for label in ('prevalence', 'population', 'incidence'):
+        assert np.array_equal(fused.final_var(label), every.var(label)), label
+    # scale-up vars keep the value of the last derivative call (TB model, drop-in var_array)
+    tb = helpers.make_model('tb')
+    tb.make_times(1900, 2050, .05)
+    tb.integrate('explicit')
+    labels = ['prevalence', 'incidence', 'mortality', 'program_rate_detect']
+    fused = tb.integrate_ensemble('explicit', n_members=3, final_vars=labels)
+    for label in labels:
+        want = tb.var_array[-1, tb.var_labels.index(label)]
+        assert np.all(fused.final_var(label) == want), label
+    assert np.array_equal(tb.var_array[::50], golden['tb_var_array_every50'])
+    # the adaptive method takes the same output
+    a = seir.integrate_ensemble('scipy', n_members=3000, final_vars=['prevalence'])
+    b = seir.integrate_ensemble('scipy', n_members=3000, output='final')
+    pop = b.final.sum(axis=0)
+    assert np.allclose(a.final_var('prevalence'), b.final[2] / pop, rtol=1e-14, atol=0)

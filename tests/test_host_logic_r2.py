@@ -177,3 +177,32 @@ def test_model_size_limits_raise_clear_errors_before_any_compilation():
         m.integrate_ensemble('discrete_time_stochastic', n_members=8, output='final')
     with pytest.raises(ValueError, match='at most 64 compartments'):
         m.integrate_ensemble('continuous_time_stochastic', n_members=8, output='stats')
+
+
+def test_final_vars_are_traced_the_way_the_diagnostics_pass_runs_them():
+    from popdynamics_b200 import capi
+    m = helpers.make_model('rmit')
+    m.check_flow_transfers()
+    cm = compiler.compile_model(m, 'explicit', final_vars=['proportion', 'population'])
+    assert cm.final_var_labels == ['proportion', 'population']
+    src = cm.cuda_source()
+    assert '#define PD_NFVAR 2' in src and 'pd_final_vars(' in src
+    kernel = capi.Model(src, capi.EXPLICIT, capi.FINAL_VARS, capi.PHILOX, 0, cm.n_comp,
+                        cm.n_param, 0, cm.n_su, cm.n_flow)
+    assert kernel.cubin()[:4] == b'\x7fELF'
+    kernel.close()
+    # same nodes as the separate diagnostics compile reaches (shared leaves, plain sum fold)
+    diag = compiler.compile_model(m, 'explicit', diagnostics=True, want_vars=['proportion'])
+    assert '#define PD_NDIAG 1' in diag.cuda_source()
+    with pytest.raises(KeyError):
+        compiler.compile_model(m, 'explicit', final_vars=['nope'])
+    with pytest.raises(ValueError, match='ODE methods'):
+        s = helpers.make_model('strains')
+        s.check_flow_transfers()
+        compiler.compile_model(s, 'discrete_time_stochastic', final_vars=['population'])
+    with pytest.raises(capi.PopdynError):              # PD_FINAL_VARS is for the ODE kernels
+        s = helpers.make_model('strains')
+        s.check_flow_transfers()
+        cs = compiler.compile_model(s, 'discrete_time_stochastic')
+        capi.Model(cs.cuda_source(), capi.TAU_LEAP, capi.FINAL_VARS, capi.PHILOX, 0, cs.n_comp,
+                   cs.n_param, 0, 0, cs.n_flow)
