@@ -479,8 +479,12 @@ class CompiledModel(object):
 
     # ---- CUDA C for NVRTC ------------------------------------------------------------------
     def cuda_source(self):
+        """The generated model header (memoised: a CompiledModel is not mutated after
+        compile_model returns)."""
         from .codegen import emit_model_header
-        return emit_model_header(self)
+        if getattr(self, '_cuda_source', None) is None:
+            self._cuda_source = emit_model_header(self)
+        return self._cuda_source
 
     def structure_key(self):
         """Hash of everything that shapes the generated kernel (NOT parameter values)."""

@@ -606,7 +606,7 @@ def integrate_hybrid(model, segments, n_members, cutoff, seed=0, member_offset=0
     res.method, res.output, res.labels = 'hybrid', output, list(model.labels)
     res.n_members, res.member_offset, res.seed, res.device = M, member_offset, seed, device
     rows, times, modes = [], [], []
-    member_blocks = {}
+    member_blocks, compiled = {}, {}
     for k, seg in enumerate(segments):
         model.make_times(*seg)
         tt = list(model.target_times)
@@ -622,7 +622,10 @@ def integrate_hybrid(model, segments, n_members, cutoff, seed=0, member_offset=0
                                      ('explicit', 1, n_explicit)):
             if not count:
                 continue
-            cm = compiler.compile_model(model, method, is_continue=(k > 0))
+            if (method, k > 0) not in compiled:    # the trace does not depend on the time grid
+                compiled[(method, k > 0)] = compiler.compile_model(model, method,
+                                                                   is_continue=(k > 0))
+            cm = compiled[(method, k > 0)]
             if method not in member_blocks:        # slot order depends on the trace
                 block_ = _member_param_block(cm, M)
                 member_blocks[method] = None if block_ is None else \
