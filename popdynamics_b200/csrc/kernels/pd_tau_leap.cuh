@@ -30,10 +30,6 @@
 #include "pd_model.h"
 #include "pd_common.cuh"
 
-#ifndef PD_TAU_SPLIT_LOOP
-#define PD_TAU_SPLIT_LOOP 0   /* experiment: a PTRS-free copy of the draw loop, chosen per warp-step */
-#endif
-
 struct PdTauLaunch {
   PdStochArgs a;
   PdUniform U;
@@ -177,17 +173,8 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
       pd_event_mults(yd, U, pm, time, (const double *)0, mult);
       pd_mask live = 0;
       int end = 0;                                          /* append cursor (list offset) */
-#if PD_TAU_SPLIT_LOOP
-      int neg = 0;                 /* OR of the codes' high words: sign set = some PTRS event */
-#endif
-#if PD_TAU_SPLIT_LOOP
-#define PD_TAU_APPEND(e, code)                                                       \
-  { const double c_ = (code); s_list[end] = c_; end += PD_BLOCK; live |= (pd_mask)1 << e; \
-    neg |= __double2hiint(c_); }
-#else
 #define PD_TAU_APPEND(e, code)                                                       \
   { s_list[end] = (code); end += PD_BLOCK; live |= (pd_mask)1 << e; }
-#endif
 #define PD_TAU_CODE(e, mean)                                                         \
   if (mean > 0.0) PD_TAU_APPEND(e, pd_tau_code(mean))                                \
   else if (!(mean == 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }
@@ -239,24 +226,6 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
     prod *= (u);                                                                     \
     if (prod > code) X += 1; else PD_TAU_NEXT(X)                                     \
   }
-#if PD_TAU_SPLIT_LOOP && PD_RNG_MODE == PD_RNG_PHILOX
-      /* no lane of the warp has a PTRS event in this step (the usual case for small means): the
-       * walk without the two sign tests per trip */
-      if (!__any_sync(__activemask(), neg < 0)) {
-        while (cur != end) {
-          if (!rng.has_spare) {
-            double u0;
-            rng.block(a, u0, rng.spare);
-            rng.has_spare = 1;
-            PD_TAU_MULT(u0)
-          }
-          if (cur != end) {
-            rng.has_spare = 0;
-            PD_TAU_MULT(rng.spare)
-          }
-        }
-      }
-#endif
       while (cur != end) {
         if (code < 0.0) {
           /* PTRS event (mean >= 10): one attempt = the next two uniforms of the same stream,
