@@ -185,3 +185,31 @@ def test_user_defined_checks_in_the_stochastic_loops_fire_like_the_reference(met
         assert (err == 1) == expect_failure
         if not expect_failure:
             assert np.array_equal(soln, theirs.soln_array)
+
+
+def test_host_derivative_closure_and_event_list_equal_the_references():
+    # make_derivate_fn (basepop.py:613-626) and calculate_events (:690-735) exist on the drop-in as
+    # host methods; the reference's unmodified example classes run on both base classes
+    for script, cls, args, y, t in (
+            ('tb_model.py', 'SimpleTbModel', ([],), [9e5, 100., 2000., 50., 20., 10.], 1985.3),
+            ('seir_model.py', 'SeirDemographyModel', (SEIR['measles'],),
+             [9e5, 20., 30., 9e4], 12.5),
+            ('rmit_tb_model.py', 'RmitTbModel', (dict(helpers.RMIT, beta=80.),),
+             [.6, .01, .05, .3, .001, .03], 3.0)):
+        theirs = reference.example_classes(script)[cls](*args)
+        ours = dropin(script, cls)(*args)
+        theirs.check_flow_transfers()
+        ours.check_flow_transfers()
+        f_theirs, f_ours = theirs.make_derivate_fn(), ours.make_derivate_fn()
+        assert f_ours(list(y), t) == f_theirs(list(y), t)
+        assert list(ours.vars.items()) == list(theirs.vars.items())      # same keys, same order
+    theirs = reference.example_classes('stochastic_strains_model.py')['StrainsModel']()
+    ours = dropin('stochastic_strains_model.py', 'StrainsModel')()
+    for m in (theirs, ours):
+        m.check_flow_transfers()
+        m.compartments = {k: int(v) for k, v in m.init_compartments.items()}
+        m.compartments['recovered_resident'] = 7
+        m.calculate_vars()
+        m.calculate_events()
+    assert ours.events == theirs.events and len(ours.events) == 9
+    assert ours.vars['rate_death'] == theirs.vars['rate_death']
