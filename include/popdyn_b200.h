@@ -250,6 +250,11 @@ int pd_philox_fill(double *out, int64_t n, int64_t n_member, int64_t member0, ui
  * half) + LOP3, and SHF + LOP3: they show what one Philox multiply costs on the FMA-heavy pipe.
  * Returns giga-operations (giga-elements) per second.                                          */
 int pd_microbench(int32_t kind, int32_t device, double *gops);
+/* Compares the kernels' own forms of exp, log and division (csrc/kernels/pd_math.cuh) with the CUDA
+ * math library's on `n` generated arguments each: n_bad[0] exp, [1] log on the 53-bit uniform
+ * grid, [2] log on raw bit patterns, [3] division; first_bad[k] is one offending argument.  All
+ * four counts must be zero: the forms are restatements, not approximations.                  */
+int pd_math_selfcheck(int32_t device, int64_t n, uint64_t seed, uint64_t *n_bad, double *first_bad);
 
 #ifdef __cplusplus
 }

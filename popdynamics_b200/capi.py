@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = (
     'pd_model_cubin_size', 'pd_model_cubin_copy', 'pd_explicit_schedule', 'pd_run_explicit',
     'pd_run_tau_leap', 'pd_run_gillespie', 'pd_run_diagnostics', 'pd_run_adaptive',
     'pd_hist_quantiles',
-    'pd_hist_moments', 'pd_philox_fill', 'pd_microbench')
+    'pd_hist_moments', 'pd_philox_fill', 'pd_microbench', 'pd_math_selfcheck')
 
 
 class ExtensionMissing(RuntimeError):
@@ -158,6 +158,7 @@ def lib():
     L.pd_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64,
                                  C.c_int32, C.c_void_p]
     L.pd_microbench.argtypes = [C.c_int32, C.c_int32, P(C.c_double)]
+    L.pd_math_selfcheck.argtypes = [C.c_int32, C.c_int64, C.c_uint64, P(C.c_uint64), P(C.c_double)]
     _lib = L
     return L
 
@@ -270,6 +271,14 @@ def hist_moments(hist, n_row, n_comp, n_bins, moments, device=0, stream=None):
 def philox_fill(out, n, n_member, member0, seed, device=0, stream=None):
     check(lib().pd_philox_fill(address(out), n, n_member, member0, seed, device, stream))
     return out
+
+
+def math_selfcheck(n, seed=0, device=0):
+    """(mismatch counts, one offending argument each) of pd_math.cuh against the math library."""
+    bad = (C.c_uint64 * 4)()
+    first = (C.c_double * 4)()
+    check(lib().pd_math_selfcheck(device, n, seed, bad, first))
+    return list(bad), list(first)
 
 
 def microbench(kind, device=0):

@@ -42,6 +42,8 @@ def _node_expr(g, node, name):
     a = name[node[1]]
     b = name[node[2]] if node[2] >= 0 else None
     c = name[node[3]] if node[3] >= 0 else None
+    if op == 'div':
+        return 'PD_DIV(%s, %s)' % (a, b)
     if op in _BIN:
         return '%s %s %s' % (a, _BIN[op], b)
     if op == 'neg':
@@ -51,7 +53,7 @@ def _node_expr(g, node, name):
     if op == 'floor':
         return 'floor(%s)' % a
     if op == 'exp':
-        return 'exp(%s)' % a
+        return 'PD_EXP(%s)' % a
     if op == 'not':
         return '!%s' % a
     if op == 'isfinite':
@@ -185,6 +187,13 @@ def emit_model_header(cm):
     w = out.append
     w('// ---- generated by popdynamics_b200/codegen.py: do not edit ----')
     w('// method: %s   compartments: %s' % (cm.method, ', '.join(cm.labels)))
+    # a kernel may supply its own forms of the traced division and exp (kernels/pd_math.cuh)
+    w('#ifndef PD_DIV')
+    w('#define PD_DIV(a, b) ((a) / (b))')
+    w('#endif')
+    w('#ifndef PD_EXP')
+    w('#define PD_EXP(x) exp(x)')
+    w('#endif')
     w('#define PD_C %d' % C)
     w('#define PD_NFLOW %d' % S)
     w('#define PD_NFLOW_DIM %d' % max(S, 1))

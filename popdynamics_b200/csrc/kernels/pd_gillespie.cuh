@@ -25,6 +25,21 @@
  * per count into the histograms, one REDUX per moment.  A lane that gets PD_GIL_SLOTS target times
  * ahead of the slowest lane of its warp waits for it; there is no block-level barrier.
  */
+/* Per-event arithmetic shaped for this kernel (pd_math.cuh), one bit each so that a build can be
+ * compared with the plain forms (POPDYN_DEFINE=-DPD_GIL_OPT=0): 1 the traced divisions skip the
+ * divider's slow path for a zero numerator, 2 dead rows are zeroed through the integer halves, 4 the
+ * traced exp and 8 the waiting-time log keep their coefficients in the constant bank.  Values
+ * are the same in every combination. */
+#ifndef PD_GIL_OPT
+#define PD_GIL_OPT 15
+#endif
+#include "pd_math.cuh"
+#if PD_GIL_OPT & 1
+#define PD_DIV(a, b) pd_div_zero_guard(a, b)
+#endif
+#if PD_GIL_OPT & 4
+#define PD_EXP(x) pd_exp_any(x)
+#endif
 #include "pd_model.h"
 #include "pd_common.cuh"
 
@@ -91,7 +106,7 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
 #define PD_ACC_FLOAT(e, live_)                                                       \
   {                                                                                  \
     const bool lv = (live_);                                                         \
-    const double rr = lv ? r[e] : 0.0;                                               \
+    const double rr = (PD_GIL_OPT & 2) ? pd_keep_if(lv, r[e]) : (lv ? r[e] : 0.0);   \
     cum += rr; cumul[e] = cum; PD_SETBIT(live, e, lv);                            \
     if (!PD_NAIVE_SUM) {                                                             \
       /* CPython's correction term (hi - t) + lo, hi the larger magnitude, IS the rounding  \
@@ -135,7 +150,7 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   if (rng.exhausted) return PD_ERR_STREAM;
   if (total == 0.0) return PD_ERR_ZERO_RATE;
   if (u2 == 0.0) return PD_ERR_LOG0;
-  const double dt = -log(u2) / total;
+  const double dt = -((PD_GIL_OPT & 8) ? pd_log_any(u2) : log(u2)) / total;
 
   /* pass 2: first live event with not (point > cumul), else the last live one (:176-177) */
   pd_u32 above[PD_GIL_WORDS];                   /* rows with point > cumul[e] */

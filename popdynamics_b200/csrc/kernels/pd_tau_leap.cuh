@@ -27,6 +27,13 @@
  *   3. APPLY PASS, lockstep again: the flow-table rows in order, compartment indices literal,
  *      clamp to the current source count and move.
  */
+/* the traced rate expressions use the guarded division and the constant-bank exp of pd_math.cuh
+ * (same values; see pd_gillespie.cuh): counts of zero are as common here */
+#include "pd_math.cuh"
+#ifndef PD_TAU_PLAIN_MATH
+#define PD_DIV(a, b) pd_div_zero_guard(a, b)
+#define PD_EXP(x) pd_exp_any(x)
+#endif
 #include "pd_model.h"
 #include "pd_common.cuh"
 

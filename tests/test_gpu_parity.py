@@ -4,6 +4,8 @@ oracle on the same seeded inputs and against the reference's golden vectors.
 Bars: explicit Euler -- bit-exact fp64 (the north-star tolerance is rel 1e-10; --fmad=false and
 preserved program order make it exact); stochastic integrators -- bit-exact integer counts, both
 under an injected uniform stream and with the native Philox streams."""
+import os
+
 import numpy as np
 import pytest
 
@@ -695,3 +697,41 @@ def test_ptrs_squeeze_never_disagrees_with_the_exact_acceptance_test(monkeypatch
                                    oracle.Rng('philox', seed=77, member=i),
                                    params=om.member_params(i))
         assert err == 0 and np.array_equal(plain.final[:, i], want[-1]), i
+
+
+# ------------------------------------------------------------------------------- pd_math.cuh
+@pytest.mark.gpu
+def test_kernel_forms_of_exp_log_and_division_equal_the_math_library_bit_for_bit():
+    """csrc/kernels/pd_math.cuh restates the library's fast paths with constant-bank coefficients
+    and guards the divider against zero numerators: 1e8 arguments per form, no differing bit."""
+    from popdynamics_b200 import capi
+    bad, first = capi.math_selfcheck(100_000_000, seed=2024)
+    assert bad == [0, 0, 0, 0], (bad, first)
+
+
+@pytest.mark.gpu
+def test_gillespie_arithmetic_forms_do_not_change_results(tmp_path):
+    """PD_GIL_OPT=0 (plain divisions, library exp / log, ternary dead rows) against the default
+    build of pd_gillespie_kernel: same events, same waiting times, member for member."""
+    import subprocess
+    import sys
+    script = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from examples import configs
+m = configs.tb_gillespie()
+m.make_times(1950, 1951, 0.25)
+res = m.integrate_ensemble('continuous_time_stochastic', n_members=4096, output='full', seed=11)
+np.save(sys.argv[1], np.asarray(res.soln.cpu() if hasattr(res.soln, 'cpu') else res.soln))
+print(int(res.info['n_steps']))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tag, define in (('plain', '-DPD_GIL_OPT=0'), ('tuned', '-DPD_GIL_OPT=15')):
+        env = dict(os.environ, POPDYN_DEFINE=define)
+        path = str(tmp_path / (tag + '.npy'))
+        done = subprocess.run([sys.executable, '-c', script, path], env=env, capture_output=True,
+                              text=True, timeout=600)
+        assert done.returncode == 0, done.stderr[-2000:]
+        outs.append((np.load(path), int(done.stdout.split()[-1])))
+    assert outs[0][1] == outs[1][1] and outs[0][1] > 0
+    assert np.array_equal(outs[0][0], outs[1][0])

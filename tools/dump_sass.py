@@ -6,11 +6,11 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from examples import models
+from examples import configs, models
 from popdynamics_b200 import capi, compiler
 
-MODELS = {'strains': models.StrainsModel, 'sir': models.SirModel, 'seir': models.SeirDemographyModel,
-          'tb': models.SimpleTbModel, 'tbsu': models.ScaleupTbModel, 'rmit': getattr(models, 'RmitTbModel', None)}
+MODELS = {'strains': models.StrainsModel, 'sir': models.SirModel, 'seir': lambda: configs.seir_sweep(0, 8),
+          'tb': models.SimpleTbModel, 'tbsu': models.ScaleupTbModel, 'rmit': lambda: configs.rmit_sweep(0, 8)}
 
 
 def main():

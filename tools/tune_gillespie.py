@@ -1,5 +1,6 @@
 """Time pd_gillespie_kernel on the TB model (config 4) over launch-geometry variants.
-usage: python tools/tune_gillespie.py [members] [years]"""
+usage: python tools/tune_gillespie.py [members] [years] [block:min_blocks,...]
+POPDYN_DEFINE=-DPD_GIL_OPT=<bits> selects the per-event arithmetic forms (kernels/pd_gillespie.cuh)."""
 import os
 import sys
 
@@ -19,8 +20,10 @@ def main():
     method = 'continuous_time_stochastic'
     cm = compiler.compile_model(model, method)
     out = torch.zeros((cm.n_comp, M), dtype=torch.float64, device='cuda')
-    for block, minb in ((256, 0), (256, 3), (256, 4), (128, 0), (128, 5), (128, 6), (128, 8),
-                        (64, 10), (64, 16)):
+    geoms = ((256, 0), (256, 3), (256, 4), (128, 0), (128, 5), (128, 6), (128, 8), (64, 10), (64, 16))
+    if len(sys.argv) > 3:
+        geoms = tuple(tuple(int(x) for x in g.split(':')) for g in sys.argv[3].split(','))
+    for block, minb in geoms:
         best = 1e30
         for _ in range(2):
             res = ensemble.run_compiled(model, cm, method, model.get_init_list(),
