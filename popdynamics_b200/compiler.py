@@ -276,10 +276,12 @@ def traced_sum(iterable, start=0, naive=False):
             continue
         x = total._lift(x)
         t = total + x
-        bigger = Sym(g, g.add('ge', g.add('fabs', total.n), g.add('fabs', x.n)), is_bool=True)
-        lo1 = (total - t) + x
-        lo2 = (x - t) + total
-        term = Sym(g, g.add('select', bigger.n, lo1.n, lo2.n))
+        # CPython's correction term -- (total - t) + x when |total| >= |x|, else (x - t) + total --
+        # is the rounding error of total + x, which is exactly representable; Knuth's TwoSum
+        # yields that same number without the comparison, the two magnitudes and the select
+        # (and the same non-finite compensation, which the end test discards, on overflow)
+        bb = t - total
+        term = (total - (t - bb)) + (x - bb)
         comp = term if comp is None else comp + term
         total = t
     if comp is not None:

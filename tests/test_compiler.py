@@ -235,3 +235,40 @@ def test_old_div_on_an_int_initial_compartment_is_rejected_for_the_ode_method():
     assert 'floor(' in cm.cuda_source()
     # the shipped examples give int initial values but never divide them
     helpers.compiled(helpers.make_model('strains'), 'explicit')
+
+
+def test_twosum_form_of_the_compensated_sum_equals_cpython_sum():
+    """traced_sum emits Knuth's TwoSum for the correction term of CPython's (>= 3.12) compensated
+    float sum instead of the magnitude comparison: the same number whenever nothing overflows,
+    and a non-finite compensation -- which the end test discards -- in the same cases otherwise."""
+    import math
+    import sys
+    if sys.version_info < (3, 12):
+        pytest.skip('builtin sum() compensates from CPython 3.12 on')
+
+    def emitted(xs):
+        total, comp = xs[0], None
+        for x in xs[1:]:
+            t = total + x
+            bb = t - total
+            term = (total - (t - bb)) + (x - bb)
+            comp = term if comp is None else comp + term
+            total = t
+        if comp is not None and comp != 0.0 and math.isfinite(comp):
+            total = total + comp
+        return total
+
+    rng = np.random.default_rng(12)
+    specials = [0.0, -0.0, 1e308, -1e308, 1.7976931348623157e308, 5e-324, float('inf'),
+                float('-inf'), float('nan')]
+    for trial in range(60000):
+        n = int(rng.integers(2, 13))
+        spread = (1, 8, 40, 300)[trial % 4]
+        xs = [float(v) for v in rng.standard_normal(n) * 10.0 ** rng.integers(-spread, spread + 1, n)]
+        if trial % 7 == 0:
+            xs = [abs(v) for v in xs]                     # rates are non-negative
+        if trial % 50 == 0:
+            xs[int(rng.integers(0, n))] = specials[int(rng.integers(0, len(specials)))]
+        want, got = sum(xs), emitted(xs)
+        assert (want == got and math.copysign(1, want) == math.copysign(1, got)) or \
+            (want != want and got != got), (xs, want, got)
