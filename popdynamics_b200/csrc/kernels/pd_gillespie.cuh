@@ -28,10 +28,11 @@
 /* Per-event arithmetic shaped for this kernel (pd_math.cuh), one bit each so that a build can be
  * compared with the plain forms (POPDYN_DEFINE=-DPD_GIL_OPT=0): 1 the traced divisions skip the
  * divider's slow path for a zero numerator, 2 dead rows are zeroed through the integer halves, 4 the
- * traced exp and 8 the waiting-time log keep their coefficients in the constant bank.  Values
- * are the same in every combination. */
+ * traced exp and 8 the waiting-time log keep their coefficients in the constant bank, 16 the picked
+ * row is applied through compile-time row masks instead of a jump table, 32 the picked row is found
+ * by counting instead of through a liveness mask.  Values are the same in every combination. */
 #ifndef PD_GIL_OPT
-#define PD_GIL_OPT 15
+#define PD_GIL_OPT 63
 #endif
 #include "pd_math.cuh"
 #if PD_GIL_OPT & 1
@@ -94,7 +95,14 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   pd_u32 live[PD_GIL_WORDS];
 #pragma unroll
   for (int w = 0; w < PD_GIL_WORDS; ++w) live[w] = 0;
+  int last_live = -1;          /* PD_GIL_OPT & 32: all pass 2 needs to know about liveness */
+  bool row0_live = false;
 #define PD_SETBIT(words, e, p) words[(e) >> 5] |= (pd_u32)(p) << ((e) & 31)
+#if PD_GIL_OPT & 32
+#define PD_MARK_LIVE(e, p) { if (p) last_live = (e); if ((e) == 0) row0_live = (p); }
+#else
+#define PD_MARK_LIVE(e, p) PD_SETBIT(live, e, p)
+#endif
 /* One row joins the running sums.  Branch-free: a dead row (rate not > 0, :712-733) adds +0.0,
  * which changes neither the cumulative sum nor the compensated one (t == f, the correction term
  * is (f - f) + 0), so every lane executes the same straight-line code and nothing has to be
@@ -102,12 +110,12 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
  * (pass 2 masks with the live bits).  Python's sum() adds its first float with a plain `+` and
  * compensates from the second one on (on_float_path). */
 #define PD_ACC_INT(e)                                                                \
-  { cum += r[e]; cumul[e] = cum; PD_SETBIT(live, e, 1); if (!PD_NAIVE_SUM) f += r[e]; }
+  { cum += r[e]; cumul[e] = cum; PD_MARK_LIVE(e, true); if (!PD_NAIVE_SUM) f += r[e]; }
 #define PD_ACC_FLOAT(e, live_)                                                       \
   {                                                                                  \
     const bool lv = (live_);                                                         \
     const double rr = (PD_GIL_OPT & 2) ? pd_keep_if(lv, r[e]) : (lv ? r[e] : 0.0);   \
-    cum += rr; cumul[e] = cum; PD_SETBIT(live, e, lv);                            \
+    cum += rr; cumul[e] = cum; PD_MARK_LIVE(e, lv);                               \
     if (!PD_NAIVE_SUM) {                                                             \
       /* CPython's correction term (hi - t) + lo, hi the larger magnitude, IS the rounding  \
        * error of f + rr, which is exactly representable; Knuth's branch-free TwoSum yields  \
@@ -129,8 +137,9 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
 #undef PD_G1_DEATH
 #undef PD_ACC_INT
 #undef PD_ACC_FLOAT
+#undef PD_MARK_LIVE
 
-  pd_u32 any = 0;
+  pd_u32 any = (PD_GIL_OPT & 32) ? (pd_u32)(last_live >= 0) : 0u;
 #pragma unroll
   for (int w = 0; w < PD_GIL_WORDS; ++w) any |= live[w];
   if (!any) {                                   /* :767-770 */
@@ -153,6 +162,32 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   const double dt = -((PD_GIL_OPT & 8) ? pd_log_any(u2) : log(u2)) / total;
 
   /* pass 2: first live event with not (point > cumul), else the last live one (:176-177) */
+  int sel = -1;
+#if PD_GIL_OPT & 32
+  {
+    /* cumul[] never decreases and a dead row repeats its predecessor's entry, so the first row
+     * with not (point > cumul) -- the NUMBER of rows with point > cumul -- raised the cumulative
+     * sum, i.e. is live, unless it sits before the first live row (cumul still 0, which takes
+     * point == 0).  No liveness mask then: a count, the index of the last live row for a point
+     * beyond every interval, and a cold search for the first live row. */
+    int n_above = 0;
+#define PD_G2_ENTRY(e, to, is_int, rate) n_above += (int)(point > cumul[e]);
+#define PD_G2_TRANSFER(e, from, to, rate) n_above += (int)(point > cumul[e]);
+#define PD_G2_DEATH(e, from, rate) n_above += (int)(point > cumul[e]);
+    PD_FOR_EACH_LIVE_ROW(PD_G2_ENTRY, PD_G2_TRANSFER, PD_G2_DEATH)
+#undef PD_G2_ENTRY
+#undef PD_G2_TRANSFER
+#undef PD_G2_DEATH
+    if (n_above >= PD_LIVE_NROW) sel = last_live;
+    else if (n_above > 0 || row0_live) sel = n_above;
+    else {
+      sel = last_live;
+#pragma unroll
+      for (int e = PD_LIVE_NROW - 1; e >= 0; --e)
+        if (cumul[e] > 0.0) sel = e;              /* the first row that raised the sum */
+    }
+  }
+#else
   pd_u32 above[PD_GIL_WORDS];                   /* rows with point > cumul[e] */
 #pragma unroll
   for (int w = 0; w < PD_GIL_WORDS; ++w) above[w] = 0;
@@ -163,8 +198,6 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
 #undef PD_G2_ENTRY
 #undef PD_G2_TRANSFER
 #undef PD_G2_DEATH
-#undef PD_SETBIT
-  int sel = -1;
 #pragma unroll
   for (int w = 0; w < PD_GIL_WORDS; ++w) {
     const pd_u32 hit = live[w] & ~above[w];
@@ -175,8 +208,38 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
     for (int w = PD_GIL_WORDS - 1; w >= 0; --w)
       if (sel < 0 && live[w]) sel = w * 32 + 31 - __clz(live[w]);
   }
+#endif
+#undef PD_SETBIT
 
   /* apply +-1 (:778-787) */
+#if (PD_GIL_OPT & 16) && PD_NFLOW_DIM <= 64
+  {
+    /* Branch-free: which rows add to / take from compartment c is a compile-time bit mask over
+     * the rows (indices are literals, the loops fold), so the update is two mask tests per
+     * compartment with every lane on.  The `if (sel == e)` chain below compiles to a jump table --
+     * an indexed constant load and an indirect branch that the warp takes once per distinct row
+     * its lanes picked (9 percent of the kernel's stall samples on the TB model). */
+#if PD_NFLOW_DIM <= 32
+    typedef pd_u32 row_mask;
+#else
+    typedef pd_u64 row_mask;
+#endif
+    row_mask gain[PD_C], loss[PD_C];
+#pragma unroll
+    for (int c = 0; c < PD_C; ++c) gain[c] = loss[c] = 0;
+#define PD_G3_ENTRY(e, to, is_int, rate) gain[to] |= (row_mask)1 << (e);
+#define PD_G3_TRANSFER(e, from, to, rate) loss[from] |= (row_mask)1 << (e); gain[to] |= (row_mask)1 << (e);
+#define PD_G3_DEATH(e, from, rate) loss[from] |= (row_mask)1 << (e);
+    PD_FOR_EACH_LIVE_ROW(PD_G3_ENTRY, PD_G3_TRANSFER, PD_G3_DEATH)
+#undef PD_G3_ENTRY
+#undef PD_G3_TRANSFER
+#undef PD_G3_DEATH
+    const row_mask picked = (row_mask)1 << sel;
+#pragma unroll
+    for (int c = 0; c < PD_C; ++c)
+      y[c] += (pd_count)((picked & gain[c]) != 0) - (pd_count)((picked & loss[c]) != 0);
+  }
+#else
 #define PD_G3_ENTRY(e, to, is_int, rate) if (sel == e) y[to] += 1;
 #define PD_G3_TRANSFER(e, from, to, rate) if (sel == e) { y[from] -= 1; y[to] += 1; }
 #define PD_G3_DEATH(e, from, rate) if (sel == e) y[from] -= 1;
@@ -184,6 +247,7 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
 #undef PD_G3_ENTRY
 #undef PD_G3_TRANSFER
 #undef PD_G3_DEATH
+#endif
 #if PD_HAS_STEP_CHECKS
   {
     /* a user-defined checks() (:789): the updated counts, the vars computed before the event */

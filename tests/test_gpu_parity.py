@@ -735,3 +735,31 @@ print(int(res.info['n_steps']))
         outs.append((np.load(path), int(done.stdout.split()[-1])))
     assert outs[0][1] == outs[1][1] and outs[0][1] > 0
     assert np.array_equal(outs[0][0], outs[1][0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('model_name,params,times', [
+    ('sir', {'population': 40, 'start_infectious': 3.}, (0, 60, 2)),   # row 0 (infection) dies out
+    ('strains', None, (0, 30, 2)),                                     # row 0 is a birth row
+])
+def test_gillespie_pick_at_the_ends_of_the_interval_table(model_name, params, times):
+    """pick_event (basepop.py:161-178) at its two edges, which the counting search of
+    pd_gillespie_kernel treats apart: u1 == 0 (point 0: the first LIVE row, also when the rows
+    before it are dead) and u1 == 1 - 2^-53 (the product may round up to the total: the last live
+    row).  Every third reaction of every member draws one of the two."""
+    method = 'continuous_time_stochastic'
+    m = helpers.make_model(model_name, **({'params': params} if params else {}))
+    m.make_times(*times)
+    n_member, n_uniform = 64, 10000
+    rng = np.random.default_rng(31)
+    u = rng.random((n_uniform, n_member))
+    edge = rng.random((n_uniform // 2, n_member))
+    u1 = u[0::2]
+    u1[edge < 1 / 6] = 0.0
+    u1[edge > 5 / 6] = 1.0 - 2.0 ** -53
+    res = m.integrate_ensemble(method, n_members=n_member, output='full', uniforms=u)
+    om = oracle.OracleModel(helpers.compiled(m, method))
+    for i in range(n_member):
+        want, _, err = om.gillespie(m.get_init_list(), m.target_times,
+                                    oracle.Rng('inject', uniforms=u[:, i].copy()))
+        assert err == 0 and np.array_equal(res.soln[:, :, i], want), i
