@@ -27,6 +27,15 @@ struct PdAdaptiveLaunch {
   PdUniform U;
 };
 
+/* err^(-1/5) of the step controller as exp(-0.2 log(err)) with the constant-bank forms of
+ * pd_math.cuh: within 2 ulp of pow(err, -0.2), which is itself only within an ulp of the libm value
+ * the CPU oracle uses (parity of this method is a tolerance, see the file header), at half the
+ * instructions of the library's general pow, once per attempted step (out of line, like pow: its
+ * temporaries must not add to the registers of the stage loop).  err == 0 gives +inf, as pow. */
+__device__ __noinline__ double pd_inv_fifth_root(double err) {
+  return pd_exp_any(-0.2 * pd_log_any(err));
+}
+
 __device__ __forceinline__ double pd_rms_scaled(const double (&v)[PD_C], const double (&scale)[PD_C]) {
   double s = 0.0;
 #pragma unroll
@@ -130,12 +139,16 @@ pd_adaptive_kernel(const __grid_constant__ PdAdaptiveLaunch L) {
       for (int c = 0; c < PD_C; ++c) {
         const double e = hs * (E1 * k1[c] + E3 * k3[c] + E4 * k4[c] + E5 * k5[c] + E6 * k6[c] +
                                E7 * k7[c]);
-        const double r = e / (atol + fmax(fabs(y[c]), fabs(yn[c])) * rtol);
+        /* e is exactly zero for a compartment at rest (a fixed point of the model, an empty
+         * class): the guarded division keeps such lanes off the divider's slow path, which a
+         * warp otherwise runs 1.6 times per step (pd_math.cuh) */
+        const double r = pd_div_zero_guard(e, atol + pd_py_max(fabs(y[c]), fabs(yn[c])) * rtol);
         s += r * r;
       }
       const double err = sqrt(s / (double)PD_C);
+      const double growth = 0.9 * pd_inv_fifth_root(err);
       if (err < 1.0) {
-        double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+        double factor = (err == 0.0) ? 10.0 : fmin(10.0, growth);
         if (rejected) factor = fmin(1.0, factor);
         rejected = false;
         /* a step shortened to reach the target says nothing about the step the error allows:
@@ -147,7 +160,7 @@ pd_adaptive_kernel(const __grid_constant__ PdAdaptiveLaunch L) {
         if (!ok_new && !bad) { bad = PD_ERR_CHECKS; bad_at = it; }      /* :623 */
       } else {
         /* NaN lands here as well: shrink */
-        const double factor = (err == err) ? fmax(0.2, 0.9 * pow(err, -0.2)) : 0.2;
+        const double factor = (err == err) ? fmax(0.2, growth) : 0.2;
         h = hs * factor;
         rejected = true;
       }
