@@ -44,6 +44,8 @@ def _node_expr(g, node, name):
     c = name[node[3]] if node[3] >= 0 else None
     if op == 'div':
         return 'PD_DIV(%s, %s)' % (a, b)
+    if op == 'ne' and g.nodes[node[2]][0] == 'const' and g.const_values[node[2]] == 0.0:
+        return 'PD_NE0(%s)' % a           # the `if c` of CPython's compensated sum()
     if op in _BIN:
         return '%s %s %s' % (a, _BIN[op], b)
     if op == 'neg':
@@ -57,7 +59,7 @@ def _node_expr(g, node, name):
     if op == 'not':
         return '!%s' % a
     if op == 'isfinite':
-        return 'pd_isfinite(%s)' % a
+        return 'PD_ISFINITE(%s)' % a
     if op == 'select':
         return '%s ? %s : %s' % (a, b, c)
     raise ValueError('cannot emit op %r' % (op,))
@@ -170,10 +172,31 @@ def _emit_dag(cm, lines, roots):
     return name
 
 
-def _emit_checks(nodes, name, lines):
+def _emit_checks(nodes, name, lines, default=False):
     lines.append('  bool ok = true;')
+    if default:
+        # the default checks() -- every compartment >= 0 (basepop.py:1016-1025) -- which a
+        # kernel may evaluate itself (pd_explicit.cuh fuses it with the clamp of the update)
+        lines.append('#ifndef PD_SKIP_DEFAULT_CHECKS')
     for n in nodes:
         lines.append('  ok = ok && %s;' % name[n])
+    if default:
+        lines.append('#endif')
+
+
+def _is_default_checks(cm):
+    """True when the checks are exactly `compartment c >= 0.0` for c = 0 .. C-1, in order: the
+    reference's own BaseModel.checks() on a float state."""
+    g = cm.graph
+    if len(cm.check_nodes) != cm.n_comp or cm.n_comp == 0:
+        return False
+    for c, n in enumerate(cm.check_nodes):
+        node = g.nodes[n]
+        if node[0] != 'ge' or g.nodes[node[1]] [0] != 'comp' or g.nodes[node[1]][1] != c:
+            return False
+        if g.nodes[node[2]][0] != 'const' or g.const_values[node[2]] != 0.0:
+            return False
+    return True
 
 
 _SIGNATURE = ('(const double (&y)[PD_C], const PdUniform& U, const double (&pm)[PD_NPM_DIM], '
@@ -206,6 +229,15 @@ def emit_model_header(cm):
     w('#define PD_INT_STATE %d' % int(cm.integer_state))
     w('#define PD_NAIVE_SUM %d' % int(cm.naive_sum))
     w('#define PD_HAS_CHECKS %d' % int(bool(cm.check_nodes)))
+    default_checks = _is_default_checks(cm)
+    w('#define PD_DEFAULT_CHECKS %d' % int(default_checks))
+    # a kernel may supply bit-test forms of these two (same truth values, kernels/pd_math.cuh)
+    w('#ifndef PD_ISFINITE')
+    w('#define PD_ISFINITE(x) pd_isfinite(x)')
+    w('#endif')
+    w('#ifndef PD_NE0')
+    w('#define PD_NE0(x) ((x) != 0.0)')
+    w('#endif')
     w('struct PdUniform { double p[PD_NPARAM_DIM]; };')
     w('__device__ __forceinline__ bool pd_isfinite(double x) '
       '{ return fabs(x) <= 1.7976931348623157e308; }')
@@ -326,7 +358,7 @@ def emit_model_header(cm):
     w('__device__ __forceinline__ bool pd_derivative' + _SIGNATURE + 'double (&f)[PD_C]) {')
     body = []
     name = _emit_dag(cm, body, list(cm.flow_node) + list(cm.check_nodes))
-    _emit_checks(cm.check_nodes, name, body)
+    _emit_checks(cm.check_nodes, name, body, default=default_checks)
     touched = [False] * C
     body.append('  double val;')
 

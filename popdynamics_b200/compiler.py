@@ -26,6 +26,7 @@ import contextlib
 import hashlib
 import math
 import numbers
+import os
 import sys
 import threading
 
@@ -239,6 +240,12 @@ def sym_old_div(a, b):
     return a / b
 
 
+# how the correction term of the compensated sum() is emitted: 'ordered' (CPython's branch, operands
+# selected first) or 'twosum' (branch-free, three additions more); same values either way.  A
+# developer knob for A/B measurements, read once at import.
+SUM_FORM = os.environ.get('POPDYN_SUM_FORM', 'ordered')
+
+
 def traced_sum(iterable, start=0, naive=False):
     """Python's builtin ``sum`` over traced floats.
 
@@ -276,12 +283,23 @@ def traced_sum(iterable, start=0, naive=False):
             continue
         x = total._lift(x)
         t = total + x
-        # CPython's correction term -- (total - t) + x when |total| >= |x|, else (x - t) + total --
-        # is the rounding error of total + x, which is exactly representable; Knuth's TwoSum
-        # yields that same number without the comparison, the two magnitudes and the select
-        # (and the same non-finite compensation, which the end test discards, on overflow)
-        bb = t - total
-        term = (total - (t - bb)) + (x - bb)
+        if SUM_FORM == 'twosum':
+            # CPython's correction term -- (total - t) + x when |total| >= |x|, else
+            # (x - t) + total -- is the rounding error of total + x, which is exactly
+            # representable; Knuth's TwoSum yields that same number without the comparison, the
+            # two magnitudes and the select (and the same non-finite compensation, which the end
+            # test discards, on overflow): five additions and no select
+            bb = t - total
+            term = (total - (t - bb)) + (x - bb)
+        else:
+            # CPython's own branch with the operands selected BEFORE the arithmetic:
+            # (big - t) + small, two additions behind one comparison and two selects.  The ODE
+            # kernels are bound by fp64 additions and multiplications; a comparison costs them
+            # next to nothing (profiles/r2_explicit_forms_ab.txt)
+            big_first = g.add('ge', g.add('fabs', total.n), g.add('fabs', x.n))
+            big = Sym(g, g.add('select', big_first, total.n, x.n))
+            small = Sym(g, g.add('select', big_first, x.n, total.n))
+            term = (big - t) + small
         comp = term if comp is None else comp + term
         total = t
     if comp is not None:

@@ -12,9 +12,41 @@
  *   y[i] = y[i] + dt * f[i], then negatives are clamped to zero (:684-687);
  *   checks() runs on the state handed to the derivative (:623).
  * Uniform loads (dt, scale-ups) are the same address for every lane: one broadcast transaction.
+ *
+ * The kernel is bound by the FP64 pipe, and a fifth of its FP64 instructions were comparisons
+ * (DSETP): per compartment the clamp `y < 0` and the default checks() `y >= 0` (:1016-1025), per
+ * traced sum() the `c != 0 and isfinite(c)` of CPython's compensated fold.  PD_EXPL_OPT moves them
+ * to the integer ALU without changing a single result:
+ *   bit 0  the two tests of the sum are exact bit tests (pd_math.cuh);
+ *   bit 1  the default checks() is fused with the clamp.  After the update z = y + dt f the next
+ *          derivative call sees clamp(z), and `clamp(z) >= 0` fails exactly when z is NaN.  One
+ *          unsigned maximum over the high words of the z decides the sub-step: below 0x7ff00000
+ *          every z is a finite number without a sign bit -- nothing to clamp, the next checks()
+ *          passes, no comparison at all.  Otherwise some z has a sign bit or an all-ones
+ *          exponent: negative finite values are clamped on the sign bit (`z < 0` is the sign
+ *          bit for anything but NaN and -0.0), and an infinity or a NaN sends the sub-step to the
+ *          fp64 comparisons themselves.  -0.0 can only come from -0.0 + -0.0 (round to nearest),
+ *          i.e. from a compartment that was -0.0 in the initial state: a member that starts
+ *          with one takes the exact path throughout.
+ * POPDYN_DEFINE=-DPD_EXPL_OPT=0 rebuilds the plain forms (tests/test_gpu_parity.py compares them).
  */
+#ifndef PD_EXPL_OPT
+#define PD_EXPL_OPT 3
+#endif
+#ifndef PD_EXPL_UNROLL
+#define PD_EXPL_UNROLL 4          /* sub-steps per trip of the inner loop */
+#endif
+#include "pd_math.cuh"
+#if PD_EXPL_OPT & 1
+#define PD_ISFINITE(x) pd_isfinite_bits(x)
+#define PD_NE0(x) pd_ne_zero_bits(x)
+#endif
+#if PD_EXPL_OPT & 2
+#define PD_SKIP_DEFAULT_CHECKS 1
+#endif
 #include "pd_model.h"
 #include "pd_common.cuh"
+#define PD_EXPL_FUSED (((PD_EXPL_OPT) & 2) && PD_DEFAULT_CHECKS)
 
 struct PdExplicitLaunch {
   PdExplicitArgs a;
@@ -46,8 +78,20 @@ pd_explicit_kernel(const __grid_constant__ PdExplicitLaunch L) {
   bool ok = true;
   int bad_at = 0;
   pd_i64 step = 0;
+#if PD_EXPL_FUSED
+  /* the first sub-step whose derivative call is handed a state that fails checks() (:623), and
+   * whether this member can hold a -0.0 */
+  pd_i64 fail_step = -1;
+  bool exact_only = false;
+#pragma unroll
+  for (int c = 0; c < PD_C; ++c) {
+    if (!(y[c] >= 0.)) fail_step = 0;
+    exact_only = exact_only || (__double2hiint(y[c]) == (int)0x80000000);
+  }
+#endif
   for (int it = 1; it < a.n_time; ++it) {                   /* :672 */
     const int n_sub = a.n_sub[it - 1];
+#pragma unroll PD_EXPL_UNROLL
     for (int s = 0; s < n_sub; ++s, ++step) {               /* :675 */
       const double dt = a.dt[step];
 #if PD_USES_TIME
@@ -60,6 +104,42 @@ pd_explicit_kernel(const __grid_constant__ PdExplicitLaunch L) {
 #else
       const double *su = (const double *)0;
 #endif
+#if PD_EXPL_FUSED
+      pd_derivative(y, L.U, pm, t, su, f);                  /* :676, default checks left out */
+      unsigned hi_top = 0;
+#pragma unroll
+      for (int c = 0; c < PD_C; ++c) {
+        y[c] = y[c] + dt * f[c];                            /* :684 */
+        hi_top = max(hi_top, (unsigned)__double2hiint(y[c]));
+      }
+      /* largest high word below 0x7ff00000: every new value is a finite number without a sign
+       * bit -- nothing to clamp (:686-687), and the next checks() passes */
+      if (exact_only || hi_top >= 0x7ff00000u) {
+        int hi_signed = 0;
+        unsigned hi_unsigned = 0;
+#pragma unroll
+        for (int c = 0; c < PD_C; ++c) {
+          const int hi = __double2hiint(y[c]);
+          hi_signed = max(hi_signed, hi);
+          hi_unsigned = max(hi_unsigned, (unsigned)hi);
+        }
+        if (exact_only || hi_signed >= 0x7ff00000 || hi_unsigned >= 0xfff00000u) {
+          /* an infinity, a NaN or a possible -0.0 among them: the comparisons themselves */
+          bool next_ok = true;
+#pragma unroll
+          for (int c = 0; c < PD_C; ++c) {
+            if (y[c] < 0.) y[c] = 0.;
+            next_ok = next_ok && (y[c] >= 0.);
+          }
+          if (!next_ok && fail_step < 0) fail_step = step + 1;
+        } else {
+          /* negative finite values (and nothing else with a sign bit): clamp on the sign bit */
+#pragma unroll
+          for (int c = 0; c < PD_C; ++c)
+            if (__double2hiint(y[c]) < 0) y[c] = 0.;
+        }
+      }
+#else
       const bool step_ok = pd_derivative(y, L.U, pm, t, su, f);   /* :676 */
       if (!step_ok && ok) { ok = false; bad_at = it; }            /* :623 */
 #pragma unroll
@@ -67,12 +147,27 @@ pd_explicit_kernel(const __grid_constant__ PdExplicitLaunch L) {
         y[c] = y[c] + dt * f[c];                            /* :684 */
         if (y[c] < 0.) y[c] = 0.;                           /* :686-687 */
       }
+#endif
     }
 #if PD_OUT_MODE == PD_OUT_FULL
 #pragma unroll
     for (int c = 0; c < PD_C; ++c) a.soln[((size_t)it * PD_C + c) * a.out_ld + m] = y[c];  /* :688 */
 #endif
   }
+#if PD_EXPL_FUSED
+  if (fail_step >= 0 && fail_step < step) {
+    /* a derivative call did see that state (the one after the last sub-step never happens):
+     * the target interval of that call, as the plain form reports it */
+    pd_i64 seen = 0;
+    int it = 1;
+    for (; it < a.n_time - 1; ++it) {
+      seen += a.n_sub[it - 1];
+      if (fail_step < seen) break;
+    }
+    ok = false;
+    bad_at = it;
+  }
+#endif
 #if PD_OUT_MODE == PD_OUT_FINAL
 #pragma unroll
   for (int c = 0; c < PD_C; ++c) a.final_state[(size_t)c * a.out_ld + m] = y[c];

@@ -237,21 +237,28 @@ def test_old_div_on_an_int_initial_compartment_is_rejected_for_the_ode_method():
     helpers.compiled(helpers.make_model('strains'), 'explicit')
 
 
-def test_twosum_form_of_the_compensated_sum_equals_cpython_sum():
-    """traced_sum emits Knuth's TwoSum for the correction term of CPython's (>= 3.12) compensated
-    float sum instead of the magnitude comparison: the same number whenever nothing overflows,
-    and a non-finite compensation -- which the end test discards -- in the same cases otherwise."""
+def test_both_forms_of_the_compensated_sum_equal_cpython_sum():
+    """traced_sum emits the correction term of CPython's (>= 3.12) compensated float sum either as
+    CPython's own magnitude branch with the operands selected before the arithmetic ('ordered',
+    the default) or as Knuth's TwoSum ('twosum', POPDYN_SUM_FORM): the same number whenever
+    nothing overflows, and a non-finite compensation -- which the end test discards -- in the
+    same cases otherwise."""
     import math
     import sys
     if sys.version_info < (3, 12):
         pytest.skip('builtin sum() compensates from CPython 3.12 on')
 
-    def emitted(xs):
+    def emitted(xs, form):
         total, comp = xs[0], None
         for x in xs[1:]:
             t = total + x
-            bb = t - total
-            term = (total - (t - bb)) + (x - bb)
+            if form == 'twosum':
+                bb = t - total
+                term = (total - (t - bb)) + (x - bb)
+            else:                                      # 'ordered': operands selected first
+                big_first = abs(total) >= abs(x)
+                big, small = (total, x) if big_first else (x, total)
+                term = (big - t) + small
             comp = term if comp is None else comp + term
             total = t
         if comp is not None and comp != 0.0 and math.isfinite(comp):
@@ -269,6 +276,8 @@ def test_twosum_form_of_the_compensated_sum_equals_cpython_sum():
             xs = [abs(v) for v in xs]                     # rates are non-negative
         if trial % 50 == 0:
             xs[int(rng.integers(0, n))] = specials[int(rng.integers(0, len(specials)))]
-        want, got = sum(xs), emitted(xs)
-        assert (want == got and math.copysign(1, want) == math.copysign(1, got)) or \
-            (want != want and got != got), (xs, want, got)
+        want = sum(xs)
+        for form in ('ordered', 'twosum'):
+            got = emitted(xs, form)
+            assert (want == got and math.copysign(1, want) == math.copysign(1, got)) or \
+                (want != want and got != got), (form, xs, want, got)
