@@ -22,6 +22,44 @@
 #include "pd_model.h"
 #include "pd_common.cuh"
 
+#ifndef PD_ADAPT_TAB
+#define PD_ADAPT_TAB 1
+#endif
+#if PD_ADAPT_TAB
+__constant__ double pd_dp_tab[30] = {
+    1.0 / 5.0,             /* A21 */
+    3.0 / 40.0,            /* A31 */
+    9.0 / 40.0,            /* A32 */
+    44.0 / 45.0,           /* A41 */
+    -56.0 / 15.0,          /* A42 */
+    32.0 / 9.0,            /* A43 */
+    19372.0 / 6561.0,      /* A51 */
+    -25360.0 / 2187.0,     /* A52 */
+    64448.0 / 6561.0,      /* A53 */
+    -212.0 / 729.0,        /* A54 */
+    9017.0 / 3168.0,       /* A61 */
+    -355.0 / 33.0,         /* A62 */
+    46732.0 / 5247.0,      /* A63 */
+    49.0 / 176.0,          /* A64 */
+    -5103.0 / 18656.0,     /* A65 */
+    35.0 / 384.0,          /* B1 */
+    500.0 / 1113.0,        /* B3 */
+    125.0 / 192.0,         /* B4 */
+    -2187.0 / 6784.0,      /* B5 */
+    11.0 / 84.0,           /* B6 */
+    -71.0 / 57600.0,       /* E1 */
+    71.0 / 16695.0,        /* E3 */
+    -71.0 / 1920.0,        /* E4 */
+    17253.0 / 339200.0,    /* E5 */
+    -22.0 / 525.0,         /* E6 */
+    1.0 / 40.0,            /* E7 */
+    1.0 / 5.0,             /* C2 */
+    3.0 / 10.0,            /* C3 */
+    4.0 / 5.0,             /* C4 */
+    8.0 / 9.0,             /* C5 */
+};
+#endif
+
 struct PdAdaptiveLaunch {
   PdAdaptiveArgs a;
   PdUniform U;
@@ -49,19 +87,72 @@ pd_adaptive_kernel(const __grid_constant__ PdAdaptiveLaunch L) {
   const pd_i64 m = (pd_i64)blockIdx.x * PD_BLOCK + threadIdx.x;
   if (m >= a.n_member) return;
 
-  /* Dormand-Prince 5(4) tableau */
+  /* Dormand-Prince 5(4) tableau: in the constant bank (PD_ADAPT_TAB, the default), so that a
+   * coefficient is a c[][] operand of its DMUL; as literals every use costs two UMOVs (92 of the
+   * 746 instructions of an attempted step) */
+#if PD_ADAPT_TAB
+#define A21 pd_dp_tab[0]
+#define A31 pd_dp_tab[1]
+#define A32 pd_dp_tab[2]
+#define A41 pd_dp_tab[3]
+#define A42 pd_dp_tab[4]
+#define A43 pd_dp_tab[5]
+#define A51 pd_dp_tab[6]
+#define A52 pd_dp_tab[7]
+#define A53 pd_dp_tab[8]
+#define A54 pd_dp_tab[9]
+#define A61 pd_dp_tab[10]
+#define A62 pd_dp_tab[11]
+#define A63 pd_dp_tab[12]
+#define A64 pd_dp_tab[13]
+#define A65 pd_dp_tab[14]
+#define B1 pd_dp_tab[15]
+#define B3 pd_dp_tab[16]
+#define B4 pd_dp_tab[17]
+#define B5 pd_dp_tab[18]
+#define B6 pd_dp_tab[19]
+#define E1 pd_dp_tab[20]
+#define E3 pd_dp_tab[21]
+#define E4 pd_dp_tab[22]
+#define E5 pd_dp_tab[23]
+#define E6 pd_dp_tab[24]
+#define E7 pd_dp_tab[25]
+#define C2 pd_dp_tab[26]
+#define C3 pd_dp_tab[27]
+#define C4 pd_dp_tab[28]
+#define C5 pd_dp_tab[29]
+#else
   const double A21 = 1.0 / 5.0;
-  const double A31 = 3.0 / 40.0, A32 = 9.0 / 40.0;
-  const double A41 = 44.0 / 45.0, A42 = -56.0 / 15.0, A43 = 32.0 / 9.0;
-  const double A51 = 19372.0 / 6561.0, A52 = -25360.0 / 2187.0, A53 = 64448.0 / 6561.0,
-               A54 = -212.0 / 729.0;
-  const double A61 = 9017.0 / 3168.0, A62 = -355.0 / 33.0, A63 = 46732.0 / 5247.0,
-               A64 = 49.0 / 176.0, A65 = -5103.0 / 18656.0;
-  const double B1 = 35.0 / 384.0, B3 = 500.0 / 1113.0, B4 = 125.0 / 192.0, B5 = -2187.0 / 6784.0,
-               B6 = 11.0 / 84.0;
-  const double E1 = -71.0 / 57600.0, E3 = 71.0 / 16695.0, E4 = -71.0 / 1920.0,
-               E5 = 17253.0 / 339200.0, E6 = -22.0 / 525.0, E7 = 1.0 / 40.0;
-  const double C2 = 1.0 / 5.0, C3 = 3.0 / 10.0, C4 = 4.0 / 5.0, C5 = 8.0 / 9.0;
+  const double A31 = 3.0 / 40.0;
+  const double A32 = 9.0 / 40.0;
+  const double A41 = 44.0 / 45.0;
+  const double A42 = -56.0 / 15.0;
+  const double A43 = 32.0 / 9.0;
+  const double A51 = 19372.0 / 6561.0;
+  const double A52 = -25360.0 / 2187.0;
+  const double A53 = 64448.0 / 6561.0;
+  const double A54 = -212.0 / 729.0;
+  const double A61 = 9017.0 / 3168.0;
+  const double A62 = -355.0 / 33.0;
+  const double A63 = 46732.0 / 5247.0;
+  const double A64 = 49.0 / 176.0;
+  const double A65 = -5103.0 / 18656.0;
+  const double B1 = 35.0 / 384.0;
+  const double B3 = 500.0 / 1113.0;
+  const double B4 = 125.0 / 192.0;
+  const double B5 = -2187.0 / 6784.0;
+  const double B6 = 11.0 / 84.0;
+  const double E1 = -71.0 / 57600.0;
+  const double E3 = 71.0 / 16695.0;
+  const double E4 = -71.0 / 1920.0;
+  const double E5 = 17253.0 / 339200.0;
+  const double E6 = -22.0 / 525.0;
+  const double E7 = 1.0 / 40.0;
+  const double C2 = 1.0 / 5.0;
+  const double C3 = 3.0 / 10.0;
+  const double C4 = 4.0 / 5.0;
+  const double C5 = 8.0 / 9.0;
+#endif
 
   double y[PD_C], pm[PD_NPM_DIM];
   pm[0] = 0.0;

@@ -30,9 +30,11 @@
  * divider's slow path for a zero numerator, 2 dead rows are zeroed through the integer halves, 4 the
  * traced exp and 8 the waiting-time log keep their coefficients in the constant bank, 16 the picked
  * row is applied through compile-time row masks instead of a jump table, 32 the picked row is found
- * by counting instead of through a liveness mask.  Values are the same in every combination. */
+ * by counting instead of through a liveness mask, 64 the first pass takes every rate as it is
+ * when one integer maximum shows that none has a sign bit, is infinite or NaN (PD_GIL_FAST below).
+ * Values are the same in every combination. */
 #ifndef PD_GIL_OPT
-#define PD_GIL_OPT 63
+#define PD_GIL_OPT 127
 #endif
 #include "pd_math.cuh"
 #if PD_GIL_OPT & 1
@@ -75,6 +77,28 @@ __device__ __forceinline__ void pd_two_uniforms(const PdStochArgs &a, PdInject &
 }
 
 #define PD_GIL_WORDS ((PD_NFLOW_DIM + 31) / 32)   /* words of a flow-table row mask */
+
+/* Compile-time facts about the flow table: does it hold an entry row (always live, :706-707), is
+ * row 0 one, does an entry row carry a Python int (sum() then starts on its exact-int path). */
+#define PD_GF_NONE3(e, from, to, rate)
+#define PD_GF_NONE2(e, from, rate)
+#define PD_GF_ANY_ENTRY(e, to, is_int, rate) | 1
+#define PD_GF_ROW0_ENTRY(e, to, is_int, rate) | ((e) == 0 ? 1 : 0)
+#define PD_GF_INT_ENTRY(e, to, is_int, rate) | ((is_int) ? 1 : 0)
+#define PD_GIL_HAS_ENTRY (0 PD_FOR_EACH_LIVE_ROW(PD_GF_ANY_ENTRY, PD_GF_NONE3, PD_GF_NONE2))
+#define PD_GIL_ROW0_ENTRY (0 PD_FOR_EACH_LIVE_ROW(PD_GF_ROW0_ENTRY, PD_GF_NONE3, PD_GF_NONE2))
+#define PD_GIL_HAS_INT_ENTRY (0 PD_FOR_EACH_LIVE_ROW(PD_GF_INT_ENTRY, PD_GF_NONE3, PD_GF_NONE2))
+/* The fast first pass.  A rate that is +0.0 or positive (+inf aside) joins the running sums
+ * exactly as the reference's filtered event list would have it: a zero adds nothing, a positive
+ * one is live.  A rate is a count (+0.0 or positive) times a multiplier, so when the unsigned
+ * maximum of the multipliers' high words is below 0x7ff00000 -- no sign bit, no infinity, no NaN
+ * anywhere -- the `r > 0` test of a row, the two selects that zero a dead row and the liveness
+ * bookkeeping (5 of a row's 21 issue slots on the TB model) do nothing and are left out;
+ * whatever pass 2 needs to know about liveness it reads off cumul[].  Any other event takes the
+ * exact pass.  Needs the counting search (bit 32) and a sum() without an
+ * exact-int prefix (with f == 0 in front of the first live rate its correction term is 0 by
+ * itself, so `on_float_path` has nothing to suppress). */
+#define PD_GIL_FAST (((PD_GIL_OPT) & 64) && ((PD_GIL_OPT) & 32) && !PD_GIL_HAS_INT_ENTRY && PD_LIVE_NROW > 0)
 
 /* one reaction: returns the error code (0 = ok); advances time, mutates y */
 __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const PdUniform &U,
@@ -131,13 +155,65 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   r[e] = rate; if (is_int) PD_ACC_INT(e) else PD_ACC_FLOAT(e, true)
 #define PD_G1_TRANSFER(e, from, to, rate) r[e] = rate; PD_ACC_FLOAT(e, r[e] > 0)
 #define PD_G1_DEATH(e, from, rate) r[e] = rate; PD_ACC_FLOAT(e, r[e] > 0)
-  PD_FOR_EACH_LIVE_ROW(PD_G1_ENTRY, PD_G1_TRANSFER, PD_G1_DEATH)
-#undef PD_G1_ENTRY
-#undef PD_G1_TRANSFER
-#undef PD_G1_DEATH
-#undef PD_ACC_INT
-#undef PD_ACC_FLOAT
-#undef PD_MARK_LIVE
+/* the exact pass: every row tested, dead rows zeroed, liveness recorded */
+#define PD_GIL_PASS1_EXACT                                                           \
+  {                                                                                  \
+    cum = 0.0; f = 0.0; comp = 0.0; on_float_path = false;                           \
+    last_live = -1; row0_live = false;                                               \
+    PD_FOR_EACH_LIVE_ROW(PD_G1_ENTRY, PD_G1_TRANSFER, PD_G1_DEATH)                   \
+  }
+#if PD_GIL_FAST
+  /* the guard, on the rows' MULTIPLIERS (the rate expressions with every count set to 1.0, which
+   * folds to the multiplier itself): counts are +0.0 or positive, so a multiplier without a sign
+   * bit, finite and not NaN gives a rate that is +0.0 or positive.  Parameters sit in the
+   * constant bank or are fixed per member: their share of the maximum leaves the event loop. */
+  unsigned top = 0u;
+  {
+    double ones[PD_C];
+#pragma unroll
+    for (int c = 0; c < PD_C; ++c) ones[c] = 1.0;
+#define PD_GM_ROW(rate)                                                              \
+  { const double (&yd)[PD_C] = ones; top = max(top, (unsigned)__double2hiint(rate)); }
+#define PD_GM_ENTRY(e, to, is_int, rate) PD_GM_ROW(rate)
+#define PD_GM_TRANSFER(e, from, to, rate) PD_GM_ROW(rate)
+#define PD_GM_DEATH(e, from, rate) PD_GM_ROW(rate)
+    PD_FOR_EACH_LIVE_ROW(PD_GM_ENTRY, PD_GM_TRANSFER, PD_GM_DEATH)
+#undef PD_GM_ENTRY
+#undef PD_GM_TRANSFER
+#undef PD_GM_DEATH
+#undef PD_GM_ROW
+  }
+  const bool fast = top < 0x7ff00000u;
+  if (fast) {
+#define PD_GF_ROW(e, rate)                                                           \
+  {                                                                                  \
+    const double r_ = (rate);                                                        \
+    const double t = cum + r_;                                                       \
+    if (!PD_NAIVE_SUM) {                                                             \
+      const double bb = t - cum;                                                     \
+      comp += (cum - (t - bb)) + (r_ - bb);                                          \
+    }                                                                                \
+    cum = t; cumul[e] = t;                                                           \
+  }
+#define PD_GF_ENTRY(e, to, is_int, rate) PD_GF_ROW(e, rate)
+#define PD_GF_TRANSFER(e, from, to, rate) PD_GF_ROW(e, rate)
+#define PD_GF_DEATH(e, from, rate) PD_GF_ROW(e, rate)
+    PD_FOR_EACH_LIVE_ROW(PD_GF_ENTRY, PD_GF_TRANSFER, PD_GF_DEATH)
+#undef PD_GF_ENTRY
+#undef PD_GF_TRANSFER
+#undef PD_GF_DEATH
+#undef PD_GF_ROW
+    f = cum;                                    /* sum()'s running value IS the cumulative one */
+    /* a live row: an entry row (always), or a rate above zero -- and rates that are all +0.0
+     * or positive add up to more than zero exactly when one of them is */
+    const bool any_fast = PD_GIL_HAS_ENTRY || cum > 0.0;
+    on_float_path = any_fast;
+    last_live = any_fast ? 0 : -1;
+  } else PD_GIL_PASS1_EXACT
+#else
+  const bool fast = false;
+  PD_GIL_PASS1_EXACT
+#endif
 
   pd_u32 any = (PD_GIL_OPT & 32) ? (pd_u32)(last_live >= 0) : 0u;
 #pragma unroll
@@ -171,20 +247,41 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
      * point == 0).  No liveness mask then: a count, the index of the last live row for a point
      * beyond every interval, and a cold search for the first live row. */
     int n_above = 0;
-#define PD_G2_ENTRY(e, to, is_int, rate) n_above += (int)(point > cumul[e]);
-#define PD_G2_TRANSFER(e, from, to, rate) n_above += (int)(point > cumul[e]);
-#define PD_G2_DEATH(e, from, rate) n_above += (int)(point > cumul[e]);
+#define PD_G2_ENTRY(e, to, is_int, rate) if (point > cumul[e]) ++n_above;
+#define PD_G2_TRANSFER(e, from, to, rate) if (point > cumul[e]) ++n_above;
+#define PD_G2_DEATH(e, from, rate) if (point > cumul[e]) ++n_above;
     PD_FOR_EACH_LIVE_ROW(PD_G2_ENTRY, PD_G2_TRANSFER, PD_G2_DEATH)
 #undef PD_G2_ENTRY
 #undef PD_G2_TRANSFER
 #undef PD_G2_DEATH
-    if (n_above >= PD_LIVE_NROW) sel = last_live;
-    else if (n_above > 0 || row0_live) sel = n_above;
-    else {
-      sel = last_live;
+    bool resolved = false;
+#if PD_GIL_FAST
+    if (fast) {
+      /* after the fast pass: a row in the middle of the table raised the sum past the point, so
+       * it is live; row 0 is live when it is an entry row or its rate is above zero.  Else the
+       * point is 0 in front of dead rows, and the first live row is the first that raised the
+       * sum (the total is above zero here, PD_ERR_ZERO_RATE has been dealt with).  A point
+       * beyond every interval does not happen with finite rates: u1 < 1, so u1 * cum <= cum. */
+      resolved = true;
+      if (n_above > 0 || PD_GIL_ROW0_ENTRY || cumul[0] > 0.0)
+        sel = n_above < PD_LIVE_NROW ? n_above : PD_LIVE_NROW - 1;
+      else {
+        sel = PD_LIVE_NROW - 1;
 #pragma unroll
-      for (int e = PD_LIVE_NROW - 1; e >= 0; --e)
-        if (cumul[e] > 0.0) sel = e;              /* the first row that raised the sum */
+        for (int e = PD_LIVE_NROW - 1; e >= 0; --e)
+          if (cumul[e] > 0.0) sel = e;
+      }
+    }
+#endif
+    if (!resolved) {
+      if (n_above >= PD_LIVE_NROW) sel = last_live;
+      else if (n_above > 0 || row0_live) sel = n_above;
+      else {
+        sel = last_live;
+#pragma unroll
+        for (int e = PD_LIVE_NROW - 1; e >= 0; --e)
+          if (cumul[e] > 0.0) sel = e;            /* the first row that raised the sum */
+      }
     }
   }
 #else
@@ -210,6 +307,13 @@ __device__ __forceinline__ int pd_gillespie_event(const PdStochArgs &a, const Pd
   }
 #endif
 #undef PD_SETBIT
+#undef PD_GIL_PASS1_EXACT
+#undef PD_G1_ENTRY
+#undef PD_G1_TRANSFER
+#undef PD_G1_DEATH
+#undef PD_ACC_INT
+#undef PD_ACC_FLOAT
+#undef PD_MARK_LIVE
 
   /* apply +-1 (:778-787) */
 #if (PD_GIL_OPT & 16) && PD_NFLOW_DIM <= 64
