@@ -487,6 +487,12 @@ def run_headline(g, args):
         frac = achieved / issue_peak
         frac_pred_on = pred_on_per * member_steps / (k_ms * 1e-3) / 1e9 / issue_peak
         traffic = float(unit['dram_bytes_per_member_step']) * member_steps
+        # the busiest pipe of the capture (FMA-heavy: the IMAD.WIDE.U32 of the Philox rounds),
+        # scaled from the capture's throughput to this run's: busy cycles per member-step are a
+        # property of the code, so the busy fraction moves with member-steps/s
+        capture_rate = float(unit['units_in_launch']) / (float(unit['duration_ms']) * 1e-3)
+        frac_pipe = float(unit['pipe_fmaheavy_pct']) / 100.0 * \
+            (member_steps / (k_ms * 1e-3)) / capture_rate
         per_unit = ('%.0f thread-instructions executed per member-step (active lanes of every '
                     'issued warp instruction; %.0f with the predicate on), measured by ncu on '
                     'this kernel (%s, %s); the SURVEY.md 8d estimate of %.0f operations is '
@@ -494,13 +500,14 @@ def run_headline(g, args):
                     % (useful_per, pred_on_per, os.path.relpath(NCU_UNIT_FILE, ROOT),
                        unit.get('capture', ''), SURVEY_OPS_PER_MEMBER_STEP))
     else:
-        achieved, frac, traffic, frac_pred_on = None, None, None, None
+        achieved, frac, traffic, frac_pred_on, frac_pipe = None, None, None, None, None
         per_unit = 'no ncu capture committed for this build (%s missing)' \
             % os.path.relpath(NCU_UNIT_FILE, ROOT)
     roofline = {
         'bound': 'issue', 'kernel': 'pd_tau_leap_kernel',
         'achieved': achieved, 'peak': issue_peak, 'unit': 'G thread-inst/s',
         'frac': frac, 'frac_pred_on': frac_pred_on, 'frac_survey_unit': survey / issue_peak,
+        'frac_bounding_pipe': frac_pipe,
         'ncu': ({k: unit.get(k) for k in ('issue_active_pct', 'lanes_per_inst',
                                           'frac_issue_x_lanes', 'pipe_fmaheavy_pct',
                                           'warp_inst_per_unit')} if unit else None),
@@ -518,8 +525,12 @@ def run_headline(g, args):
         'note': 'neither HBM- nor tensor-bound: streaming-statistics mode moves ~0 B per '
                 'member-step, and even full-trajectory output (8*C B per member-step) has an '
                 'HBM ceiling ~10x above what the Poisson draws allow; the bound is instruction '
-                'issue, and inside it the FMA-heavy pipe: IMAD.WIDE.U32 (two per Philox round) '
-                'issues once per 4 cycles per scheduler on B200 (pd_microbench kinds 2-4)',
+                'issue, and inside it the integer datapath: IMAD.WIDE.U32 (two per Philox round) '
+                'holds the FMA-heavy pipe for 4 cycles per scheduler and every further ALU '
+                'instruction adds 2 more instead of hiding behind it (pd_microbench kinds 2-4, '
+                '9-10: profiles/r2_coissue_probe.jsonl).  frac = executed thread-instructions '
+                'over the issue peak (issue-active x lanes per instruction); frac_bounding_pipe '
+                '= busy fraction of the busiest pipe (FMA-heavy) as ncu measured it',
     }
     cpu = port_baseline(args.cpu_seconds)
     try:
