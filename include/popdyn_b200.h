@@ -248,6 +248,9 @@ int pd_philox_fill(double *out, int64_t n, int64_t n_member, int64_t member0, ui
  * 2 = int32 IMAD/LOP3 mix as in Philox (3 operations per element, issued as IMAD.WIDE.U32 + LOP3).
  * Kinds 3, 4, 5 count ELEMENTS per second of a dependent chain of IMAD.HI.U32 + LOP3, IMAD (low
  * half) + LOP3, and SHF + LOP3: they show what one Philox multiply costs on the FMA-heavy pipe.
+ * Kinds 6 .. 10 are co-issue probes, elements per second again: 6 = DADD alone, 7 / 8 = DADD with
+ * one / two LOP3 on chains of their own, 9 / 10 = IMAD.WIDE.U32 + LOP3 with one / two more LOP3:
+ * they show what hides behind a two-cycle fp64 or a four-cycle wide-multiply issue and what adds up.
  * Returns giga-operations (giga-elements) per second.                                          */
 int pd_microbench(int32_t kind, int32_t device, double *gops);
 /* Compares the kernels' own forms of exp, log and division (csrc/kernels/pd_math.cuh) with the CUDA
