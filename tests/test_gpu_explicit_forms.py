@@ -85,7 +85,7 @@ def test_explicit_integer_forms_do_not_change_results(tmp_path):
         assert got['rmit_err'][0] == ref['rmit_err'][0]
 
 
-def _one_member(model, y0=None):
+def _one_member(model):
     """One member through the kernel (default build) and through the oracle: trajectory, error
     flag, failing target index."""
     model.check_flow_transfers()
@@ -104,7 +104,7 @@ def test_explicit_fused_checks_on_the_edges(case):
     """States the fast path must hand to the exact comparisons, one member each, against the
     oracle: the trajectory (signs of zeros included), whether checks() fails and at which target
     index (the interval of the first derivative call that is handed a NaN, basepop.py:623)."""
-    params, times = {}, (0, 6, 1)
+    times = (0, 6, 1)
     m = helpers.make_model('sir')
     if case == 'minus_zero_at_rest':
         # nobody infectious: every flow is (+-)0, the immune class stays -0.0 (-0.0 + -0.0 only

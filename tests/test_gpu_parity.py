@@ -711,8 +711,9 @@ def test_kernel_forms_of_exp_log_and_division_equal_the_math_library_bit_for_bit
 
 @pytest.mark.gpu
 def test_gillespie_arithmetic_forms_do_not_change_results(tmp_path):
-    """PD_GIL_OPT=0 (plain divisions, library exp / log, ternary dead rows) against the default
-    build of pd_gillespie_kernel: same events, same waiting times, member for member."""
+    """PD_GIL_OPT=0 (plain divisions, library exp / log, ternary dead rows) against the later
+    builds of pd_gillespie_kernel up to the default (127: + row masks, counting search, fast
+    first pass): same events, same waiting times, member for member."""
     import subprocess
     import sys
     script = r'''
@@ -726,15 +727,41 @@ np.save(sys.argv[1], np.asarray(res.soln.cpu() if hasattr(res.soln, 'cpu') else 
 print(int(res.info['n_steps']))
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for tag, define in (('plain', '-DPD_GIL_OPT=0'), ('tuned', '-DPD_GIL_OPT=15')):
+    for tag, define in (('plain', '-DPD_GIL_OPT=0'), ('tuned', '-DPD_GIL_OPT=15'),
+                        ('counting', '-DPD_GIL_OPT=63'), ('fast_pass', '-DPD_GIL_OPT=127')):
         env = dict(os.environ, POPDYN_DEFINE=define)
         path = str(tmp_path / (tag + '.npy'))
         done = subprocess.run([sys.executable, '-c', script, path], env=env, capture_output=True,
                               text=True, timeout=600)
         assert done.returncode == 0, done.stderr[-2000:]
         outs.append((np.load(path), int(done.stdout.split()[-1])))
-    assert outs[0][1] == outs[1][1] and outs[0][1] > 0
-    assert np.array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1] > 0
+    for soln, n_events in outs[1:]:
+        assert n_events == outs[0][1]
+        assert np.array_equal(soln, outs[0][0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('recover', [-0.1, float('nan'), -0.0, 0.0])
+def test_gillespie_fast_pass_hands_odd_multipliers_to_the_exact_pass(recover):
+    """The fast first pass of pd_gillespie_kernel takes every rate as it is when no row multiplier
+    has a sign bit, is infinite or NaN; a negative, NaN or -0.0 multiplier makes rates that
+    `val > 0` (basepop.py:718) must filter, so those events take the exact pass.  SIR with such a
+    recovery rate (the row is never live), injected stream, against the oracle member by member."""
+    method = 'continuous_time_stochastic'
+    m = helpers.make_model('sir', params={'population': 60, 'start_infectious': 4.})
+    m.set_param('infection_rate_recover', recover)
+    m.make_times(0, 20, 2)
+    n_member, n_uniform = 48, 4000
+    u = np.random.default_rng(77).random((n_uniform, n_member))
+    res = m.integrate_ensemble(method, n_members=n_member, output='full', uniforms=u)
+    om = oracle.OracleModel(helpers.compiled(m, method))
+    for i in range(n_member):
+        rng = oracle.Rng('inject', uniforms=u[:, i].copy())
+        want, _, err = om.gillespie(m.get_init_list(), m.target_times, rng)
+        assert err == 0
+        assert np.array_equal(res.soln[:, :, i], want), 'member %d differs' % i
+    assert (np.asarray(res.soln)[-1, 2] == 0).all()          # nobody ever recovers
 
 
 @pytest.mark.gpu
