@@ -15,8 +15,9 @@
  *
  * The kernel is bound by the FP64 pipe, and a fifth of its FP64 instructions were comparisons
  * (DSETP): per compartment the clamp `y < 0` and the default checks() `y >= 0` (:1016-1025), per
- * traced sum() the `c != 0 and isfinite(c)` of CPython's compensated fold.  PD_EXPL_OPT moves them
- * to the integer ALU without changing a single result:
+ * traced sum() the `c != 0 and isfinite(c)` of CPython's compensated fold.  PD_EXPL_OPT takes them
+ * out of the common path without changing a single result (moving a comparison to the integer
+ * ALU alone bought little, leaving instructions out is what paid: DESIGN.md 3.3):
  *   bit 0  the two tests of the sum are exact bit tests (pd_math.cuh);
  *   bit 1  the default checks() is fused with the clamp.  After the update z = y + dt f the next
  *          derivative call sees clamp(z), and `clamp(z) >= 0` fails exactly when z is NaN.  One
@@ -28,7 +29,7 @@
  *          fp64 comparisons themselves.  -0.0 can only come from -0.0 + -0.0 (round to nearest),
  *          i.e. from a compartment that was -0.0 in the initial state: a member that starts
  *          with one takes the exact path throughout.
- * POPDYN_DEFINE=-DPD_EXPL_OPT=0 rebuilds the plain forms (tests/test_gpu_parity.py compares them).
+ * POPDYN_DEFINE=-DPD_EXPL_OPT=0 rebuilds the plain forms (tests/test_gpu_explicit_forms.py compares them).
  */
 #ifndef PD_EXPL_OPT
 #define PD_EXPL_OPT 3
