@@ -111,6 +111,48 @@ __device__ __forceinline__ void pd_park_draw(double *cell, int x) {
   else *(pd_i64 *)cell = (pd_i64)x;
 }
 
+/* PD_TAU_ABS_CURSOR: the draw list is walked with 32-bit shared-memory ADDRESSES instead of
+ * element offsets from the lane's column: an access is then [register] with no multiply-add in
+ * front of it (one IMAD per appended code, per finished event and per row of the apply pass). */
+#ifndef PD_TAU_ABS_CURSOR
+#define PD_TAU_ABS_CURSOR 3
+#endif
+#if PD_TAU_ABS_CURSOR
+typedef unsigned pd_cursor;
+#define PD_CURSOR_STEP ((unsigned)(PD_BLOCK * sizeof(double)))
+__device__ __forceinline__ double pd_list_code(pd_cursor at) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(at) : "memory");
+  return v;
+}
+__device__ __forceinline__ void pd_list_put_code(pd_cursor at, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" :: "r"(at), "d"(v) : "memory");
+}
+__device__ __forceinline__ void pd_list_park(pd_cursor at, pd_i64 k) {
+  if (sizeof(pd_count) == 4) {
+    const int d = (k > 0x7fffffffLL) ? 0x7fffffff : (int)k;
+    asm volatile("st.shared.s32 [%0], %1;" :: "r"(at), "r"(d) : "memory");
+  } else asm volatile("st.shared.s64 [%0], %1;" :: "r"(at), "l"(k) : "memory");
+}
+__device__ __forceinline__ void pd_list_park(pd_cursor at, int x) {
+  if (sizeof(pd_count) == 4) asm volatile("st.shared.s32 [%0], %1;" :: "r"(at), "r"(x) : "memory");
+  else asm volatile("st.shared.s64 [%0], %1;" :: "r"(at), "l"((pd_i64)x) : "memory");
+}
+__device__ __forceinline__ pd_count pd_list_draw(pd_cursor at) {
+  if (sizeof(pd_count) == 4) {
+    int d;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(d) : "r"(at) : "memory");
+    return (pd_count)d;
+  }
+  pd_i64 d;
+  asm volatile("ld.shared.s64 %0, [%1];" : "=l"(d) : "r"(at) : "memory");
+  return (pd_count)d;
+}
+#else
+typedef int pd_cursor;
+#define PD_CURSOR_STEP PD_BLOCK
+#endif
+
 extern "C" __global__ void __launch_bounds__(PD_BLOCK, PD_MIN_BLOCKS)
 pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   const PdStochArgs &a = L.a;
@@ -135,6 +177,20 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 
   extern __shared__ double s_dyn[];
   double *const s_list = s_dyn + tid;                       /* [k][PD_BLOCK], this lane's column */
+#if PD_TAU_ABS_CURSOR
+  const pd_cursor list0 = (pd_cursor)__cvta_generic_to_shared(s_list);
+#define PD_LIST_CODE(at) pd_list_code(at)
+#define PD_LIST_PUT_CODE(at, v) pd_list_put_code(at, v)
+#define PD_LIST_PARK(at, d) pd_list_park(at, d)
+#define PD_LIST_DRAW(at) pd_list_draw(at)
+#else
+  const pd_cursor list0 = 0;
+#define PD_LIST_CODE(at) s_list[at]
+#define PD_LIST_PUT_CODE(at, v) s_list[at] = (v)
+#define PD_LIST_PARK(at, d) pd_park_draw(&s_list[at], d)
+#define PD_LIST_DRAW(at)                                                             \
+  ((sizeof(pd_count) == 4) ? (pd_count)*(const int *)&s_list[at] : (pd_count)*(const pd_i64 *)&s_list[at])
+#endif
 #if PD_OUT_MODE == PD_OUT_STATS
   __shared__ PdStatsPart s_acc;
 #endif
@@ -179,9 +235,9 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
       for (int c = 0; c < PD_C; ++c) yd[c] = (double)y[c];
       pd_event_mults(yd, U, pm, time, (const double *)0, mult);
       pd_mask live = 0;
-      int end = 0;                                          /* append cursor (list offset) */
+      pd_cursor end = list0;                                /* append cursor */
 #define PD_TAU_APPEND(e, code)                                                       \
-  { s_list[end] = (code); end += PD_BLOCK; live |= (pd_mask)1 << e; }
+  { PD_LIST_PUT_CODE(end, code); end += PD_CURSOR_STEP; live |= (pd_mask)1 << e; }
 #define PD_TAU_CODE(e, mean)                                                         \
   if (mean > 0.0) PD_TAU_APPEND(e, pd_tau_code(mean))                                \
   else if (!(mean == 0.0)) { if (!bad) bad = PD_ERR_POISSON_MEAN; }
@@ -216,16 +272,24 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 
       /* ---- 2. draw loop.  Lane state: list cursor, the current event's code, its running
        * product and count */
-      int cur = 0;
-      double code = s_list[0];
+      pd_cursor cur = list0;
+      double code = PD_LIST_CODE(list0);
       double prod = 1.0;
       int X = 0;
-/* the current event ends with draw d: park it, step to the lane's next event */
+/* the current event ends with draw d: park it, step to the lane's next event.  The advanced
+ * cursor is made opaque: otherwise the compiler, knowing it equals `end` on the other side of the
+ * test, rebuilds it as a select between `end` and the sum (two instructions instead of none) */
+#if PD_TAU_ABS_CURSOR & 2
+#define PD_TAU_OPAQUE(x) asm volatile("" : "+r"(x))
+#else
+#define PD_TAU_OPAQUE(x)
+#endif
 #define PD_TAU_NEXT(d)                                                               \
   {                                                                                  \
-    pd_park_draw(&s_list[cur], d);                                                   \
-    cur += PD_BLOCK;                                                                 \
-    if (cur != end) { code = s_list[cur]; prod = 1.0; X = 0; }                       \
+    PD_LIST_PARK(cur, d);                                                            \
+    cur += PD_CURSOR_STEP;                                                           \
+    PD_TAU_OPAQUE(cur);                                                              \
+    if (cur != end) { code = PD_LIST_CODE(cur); prod = 1.0; X = 0; }                 \
   }
 /* one uniform of the multiplication method */
 #define PD_TAU_MULT(u)                                                               \
@@ -276,6 +340,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
       }
 #undef PD_TAU_MULT
 #undef PD_TAU_NEXT
+#undef PD_TAU_OPAQUE
 
       /* ---- 3. apply pass, flow-table order: clamp to the CURRENT source count (:833-834,
        * :839-840), move; births unclamped (:842-844).  Branch-free: a row that is not in the
@@ -284,14 +349,13 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
        * updated count is checked once per step and raises the error flag (numpy / Python ints
        * never wrap). */
       if (!rng.exhausted) {
-        int get = 0;
+        pd_cursor get = list0;
         pd_count signs = 0;
 #define PD_TAU_TAKE(e, d)                                                            \
   const bool on_##e = (live >> e) & 1;                                               \
   pd_count d = 0;                                                                    \
-  if (on_##e) d = (sizeof(pd_count) == 4) ? (pd_count)*(const int *)&s_list[get]     \
-                                          : (pd_count)*(const pd_i64 *)&s_list[get]; \
-  get += on_##e ? PD_BLOCK : 0;
+  if (on_##e) d = PD_LIST_DRAW(get);                                                 \
+  get += on_##e ? PD_CURSOR_STEP : 0;
 #define PD_TAU_ENTRY(e, to, is_int, rate)                                            \
   { PD_TAU_TAKE(e, d) y[to] += d; signs |= y[to]; }
 #define PD_TAU_TRANSFER(e, from, to, rate)                                           \
