@@ -117,6 +117,9 @@ __device__ __forceinline__ void pd_park_draw(double *cell, int x) {
 #ifndef PD_TAU_ABS_CURSOR
 #define PD_TAU_ABS_CURSOR 3
 #endif
+#ifndef PD_TAU_ONE_TABLE_TEST
+#define PD_TAU_ONE_TABLE_TEST 1   /* hoist the rows' "count inside the code table" tests */
+#endif
 #if PD_TAU_ABS_CURSOR
 typedef unsigned pd_cursor;
 #define PD_CURSOR_STEP ((unsigned)(PD_BLOCK * sizeof(double)))
@@ -261,7 +264,54 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   } else { const double mean = rate * dt; PD_TAU_CODE(e, mean) }
 #define PD_TAU_TRANSFER(e, from, to, rate) PD_TAU_FIXED(e, from, rate)
 #define PD_TAU_DEATH(e, from, rate) PD_TAU_FIXED(e, from, rate)
+#if PD_TAU_ONE_TABLE_TEST && PD_NTAB > 0
+      /* One test per step instead of one per row: when the launch has a table for this dt and
+       * the largest count a table row looks up is inside it, every such row is a plain lookup
+       * (PD_TAU_LOOKUP*); any other step takes the general rows, which test and fall back to
+       * computing the code row by row. */
+      bool all_in_table = false;
+      if (use_table) {
+        pd_count top = 0;
+#define PD_TAU_TOP_ENTRY(e, to, is_int, rate)
+#define PD_TAU_TOP_FIXED(e, from) if (PD_ROW_TAB_##e >= 0) top = top > y[from] ? top : y[from];
+#define PD_TAU_TOP_TRANSFER(e, from, to, rate) PD_TAU_TOP_FIXED(e, from)
+#define PD_TAU_TOP_DEATH(e, from, rate) PD_TAU_TOP_FIXED(e, from)
+        PD_FOR_EACH_LIVE_ROW(PD_TAU_TOP_ENTRY, PD_TAU_TOP_TRANSFER, PD_TAU_TOP_DEATH)
+#undef PD_TAU_TOP_ENTRY
+#undef PD_TAU_TOP_FIXED
+#undef PD_TAU_TOP_TRANSFER
+#undef PD_TAU_TOP_DEATH
+        all_in_table = top < (pd_count)a.code_table_n;       /* counts are never negative */
+      }
+      if (all_in_table) {
+#define PD_TAU_LOOKUP_FIXED(e, from, rate)                                           \
+  if (PD_ROW_TAB_##e >= 0) {                                                         \
+    const double code = a.code_table[(PD_ROW_TAB_##e < 0 ? 0 : PD_ROW_TAB_##e) *     \
+                                     a.code_table_n + (int)y[from]];                 \
+    if (code != 0.0) PD_TAU_APPEND(e, code)                                          \
+  } else PD_TAU_COMPUTED(e, rate)
+#define PD_TAU_LOOKUP_ENTRY(e, to, is_int, rate)                                     \
+  if (PD_ROW_UNI_##e >= 0) {                                                         \
+    const double code = a.code_table[PD_NTAB * a.code_table_n +                      \
+                                     (PD_ROW_UNI_##e < 0 ? 0 : PD_ROW_UNI_##e)];     \
+    if (code != 0.0) {                                                               \
+      if (code != code) { if (!bad) bad = PD_ERR_POISSON_MEAN; }                     \
+      else PD_TAU_APPEND(e, code)                                                    \
+    }                                                                                \
+  } else { const double mean = rate * dt; PD_TAU_CODE(e, mean) }
+#define PD_TAU_LOOKUP_TRANSFER(e, from, to, rate) PD_TAU_LOOKUP_FIXED(e, from, rate)
+#define PD_TAU_LOOKUP_DEATH(e, from, rate) PD_TAU_LOOKUP_FIXED(e, from, rate)
+        PD_FOR_EACH_LIVE_ROW(PD_TAU_LOOKUP_ENTRY, PD_TAU_LOOKUP_TRANSFER, PD_TAU_LOOKUP_DEATH)
+#undef PD_TAU_LOOKUP_ENTRY
+#undef PD_TAU_LOOKUP_FIXED
+#undef PD_TAU_LOOKUP_TRANSFER
+#undef PD_TAU_LOOKUP_DEATH
+      } else {
+        PD_FOR_EACH_LIVE_ROW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
+      }
+#else
       PD_FOR_EACH_LIVE_ROW(PD_TAU_ENTRY, PD_TAU_TRANSFER, PD_TAU_DEATH)
+#endif
 #undef PD_TAU_ENTRY
 #undef PD_TAU_TRANSFER
 #undef PD_TAU_DEATH
