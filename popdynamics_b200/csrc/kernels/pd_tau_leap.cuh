@@ -115,8 +115,9 @@ __device__ __forceinline__ void pd_park_draw(double *cell, int x) {
  * element offsets from the lane's column: an access is then [register] with no multiply-add in
  * front of it (one IMAD per appended code, per finished event and per row of the apply pass). */
 #ifndef PD_TAU_ABS_CURSOR
-#define PD_TAU_ABS_CURSOR 3
+#define PD_TAU_ABS_CURSOR 1
 #endif
+
 #ifndef PD_TAU_ONE_TABLE_TEST
 #define PD_TAU_ONE_TABLE_TEST 1   /* hoist the rows' "count inside the code table" tests */
 #endif
@@ -326,19 +327,12 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
       double code = PD_LIST_CODE(list0);
       double prod = 1.0;
       int X = 0;
-/* the current event ends with draw d: park it, step to the lane's next event.  The advanced
- * cursor is made opaque: otherwise the compiler, knowing it equals `end` on the other side of the
- * test, rebuilds it as a select between `end` and the sum (two instructions instead of none) */
-#if PD_TAU_ABS_CURSOR & 2
-#define PD_TAU_OPAQUE(x) asm volatile("" : "+r"(x))
-#else
-#define PD_TAU_OPAQUE(x)
-#endif
+/* the current event ends with draw d: park it, step to the lane's next event */
+#define PD_TAU_MORE (cur != end)
 #define PD_TAU_NEXT(d)                                                               \
   {                                                                                  \
     PD_LIST_PARK(cur, d);                                                            \
     cur += PD_CURSOR_STEP;                                                           \
-    PD_TAU_OPAQUE(cur);                                                              \
     if (cur != end) { code = PD_LIST_CODE(cur); prod = 1.0; X = 0; }                 \
   }
 /* one uniform of the multiplication method */
@@ -347,7 +341,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
     prod *= (u);                                                                     \
     if (prod > code) X += 1; else PD_TAU_NEXT(X)                                     \
   }
-      while (cur != end) {
+      while (PD_TAU_MORE) {
         if (code < 0.0) {
           /* PTRS event (mean >= 10): one attempt = the next two uniforms of the same stream,
            * judged out of line; the lane rejoins the block-wise walk at the next trip */
@@ -378,7 +372,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
           rng.has_spare = 1;
           PD_TAU_MULT(u0)
         }
-        if (cur != end && code >= 0.0) {    /* the block's second uniform, or the pending spare */
+        if (PD_TAU_MORE && code >= 0.0) {   /* the block's second uniform, or the pending spare */
           rng.has_spare = 0;
           PD_TAU_MULT(rng.spare)
         }
@@ -390,7 +384,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
       }
 #undef PD_TAU_MULT
 #undef PD_TAU_NEXT
-#undef PD_TAU_OPAQUE
+#undef PD_TAU_MORE
 
       /* ---- 3. apply pass, flow-table order: clamp to the CURRENT source count (:833-834,
        * :839-840), move; births unclamped (:842-844).  Branch-free: a row that is not in the
