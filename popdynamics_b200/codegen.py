@@ -309,7 +309,22 @@ def emit_model_header(cm):
     # the table of that row (one table per distinct parameter slot), -1 for the other rows.
     # An entry row whose rate is a uniform parameter / constant has ONE code per dt for the whole
     # ensemble: PD_ROW_UNI_<row> is its slot behind the tables, -1 for the other rows.
+    # A transfer / death row whose rate is count * (count' * uniform parameter) -- a force of
+    # infection -- has a code that depends on two integer counts: PD_ROW_TAB2_<row> is its pair
+    # table (one per distinct (compartment, parameter) inside the rate), PD_ROW_TAB2B_<row> the
+    # compartment inside the rate, -1 for the other rows.
     tau_rows, tab_params, row_tab, uni_rates, row_uni = [], [], [], [], []
+    tab2_keys, row_tab2 = [], []
+
+    def pair_of(node):
+        """(compartment, uniform parameter slot) when `node` is comp * param or param * comp."""
+        if node[0] != 'mul':
+            return None
+        x, y = g.nodes[node[1]], g.nodes[node[2]]
+        for c_node, p_node in ((x, y), (y, x)):
+            if c_node[0] == 'comp' and p_node[0] == 'param' and p_node[1] not in member_slot:
+                return (c_node[1], p_node[1])
+        return None
     for e in range(S):
         if never_fires(e):
             continue
@@ -322,6 +337,13 @@ def emit_model_header(cm):
             row_tab.append(tab_params.index(node[1]))
         else:
             row_tab.append(-1)
+        pair = pair_of(node) if (kind != ENTRY and cm.integer_state) else None
+        if pair is not None:
+            if pair not in tab2_keys:
+                tab2_keys.append(pair)
+            row_tab2.append((tab2_keys.index(pair), pair[0]))
+        else:
+            row_tab2.append((-1, -1))
         if kind == ENTRY and uniform_leaf:
             row_uni.append(len(uni_rates))
             uni_rates.append(rate_expr[e])
@@ -345,6 +367,13 @@ def emit_model_header(cm):
     w('#define PD_TAB_PARAMS { %s }' % (', '.join(str(k) for k in tab_params) or '0'))
     for r, t in enumerate(row_tab):
         w('#define PD_ROW_TAB_%d %d' % (r, t))
+    w('#define PD_NTAB2 %d' % len(tab2_keys))
+    w('#define PD_NTAB2_DIM %d' % max(len(tab2_keys), 1))
+    w('#define PD_TAB2_COMPS { %s }' % (', '.join(str(c) for c, _ in tab2_keys) or '0'))
+    w('#define PD_TAB2_PARAMS { %s }' % (', '.join(str(k) for _, k in tab2_keys) or '0'))
+    for r, (t, b) in enumerate(row_tab2):
+        w('#define PD_ROW_TAB2_%d %d' % (r, t))
+        w('#define PD_ROW_TAB2B_%d %d' % (r, b))
     w('#define PD_NUNI %d' % len(uni_rates))
     w('#define PD_NUNI_DIM %d' % max(len(uni_rates), 1))
     w('#define PD_UNI_RATES { %s }' % (', '.join(uni_rates) or '0.0'))

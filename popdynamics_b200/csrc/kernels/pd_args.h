@@ -74,6 +74,12 @@ typedef struct {
   long long pm_ld;             /* row stride (elements) of pm: M, or the chunk size when the host
                                   staged this launch's member range on its own                   */
   long long out_ld;            /* row stride of soln / final_state                               */
+  const double *code_table2;   /* tau-leap: [PD_NTAB2][code_table2_nb][code_table2_na] Poisson
+                                  codes of the count x count x uniform-parameter rows (a force
+                                  of infection: susceptibles x infectious x beta), for the same
+                                  dt as code_table; NULL when not built                          */
+  int code_table2_na;          /* counts of the row's own compartment covered                    */
+  int code_table2_nb;          /* counts of the compartment inside the rate                      */
 } PdStochArgs;
 
 /* The tau-leap kernel keeps per-warp partial moment sums in shared memory and moves them to

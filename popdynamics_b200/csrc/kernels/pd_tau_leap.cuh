@@ -99,6 +99,32 @@ extern "C" __global__ void pd_tau_table_kernel(const __grid_constant__ PdTauLaun
   }
 }
 
+/* Pair tables: a row whose rate is count_a * (count_b * U.p[k]) -- the model's `rate_force = beta *
+ * infectious` var times the susceptibles -- has a code that depends on the two integer counts
+ * alone while dt is constant.  Exactly the expressions of pd_event_mults (count_b * parameter,
+ * either order: the product is the same double) and of the rate pass (count_a * that, the mean,
+ * pd_tau_code), so a looked-up code is bit-identical to a computed one; 0.0 = the row does not
+ * fire.  Layout [table][n_b][n_a], count_a fastest. */
+extern "C" __device__ unsigned int pd_tab2_count = PD_NTAB2;
+__device__ const int pd_tab2_param[PD_NTAB2_DIM] = PD_TAB2_PARAMS;
+
+extern "C" __global__ void pd_tau_table2_kernel(const __grid_constant__ PdTauLaunch L, double *table,
+                                                int n_a, int n_b, double dt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_a * n_b) return;
+  const int na = (int)(i % n_a), nb = (int)(i / n_a);
+  for (int t = 0; t < PD_NTAB2; ++t) {
+    const double mult = (double)nb * L.U.p[pd_tab2_param[t]];
+    const double rate = (double)na * mult;
+    double code = 0.0;
+    if (rate > 0) {
+      const double mean = rate * dt;          /* dt > 0: positive, zero (underflow) or +inf */
+      if (mean > 0.0) code = pd_tau_code(mean);
+    }
+    table[(size_t)t * n_a * n_b + (size_t)i] = code;
+  }
+}
+
 /* a finished draw is parked in the list cell of its code; with 32-bit counts it saturates at
  * 2^31 - 1, which changes nothing: a clamp brings it down to a count anyway and an unclamped
  * gain of that size raises PD_ERR_COUNT_RANGE either way */
@@ -231,6 +257,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
       const double dt = a.target[it] - a.target[it - 1];    /* :820 */
       const bool use_table = (PD_NTAB + PD_NUNI) > 0 && a.code_table != 0 &&
                              dt == a.code_table_dt;
+      const bool use_table2 = PD_NTAB2 > 0 && a.code_table2 != 0 && dt == a.code_table_dt;
 
       /* ---- 1. rate pass (:822-824): start-of-step counts as doubles; every rate of this step
        * is formed from them, the live counts only enter through the clamps (:833-841) */
@@ -248,11 +275,21 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #define PD_TAU_COMPUTED(e, rate)                                                     \
   { const double r_ = rate; if (r_ > 0) { const double mean = r_ * dt; PD_TAU_CODE(e, mean) } }
 /* a row of the form count * uniform parameter: looked up by count when the launch has a table */
+/* 32-bit index arithmetic: the host builds pair tables of fewer than 2^31 cells in all */
+#define PD_TAU_PAIR_INDEX(e, from)                                                   \
+  (((unsigned)(PD_ROW_TAB2_##e < 0 ? 0 : PD_ROW_TAB2_##e) * (unsigned)a.code_table2_nb + \
+    (unsigned)y[PD_ROW_TAB2B_##e < 0 ? 0 : PD_ROW_TAB2B_##e]) * (unsigned)a.code_table2_na + \
+   (unsigned)y[from])
 #define PD_TAU_FIXED(e, from, rate)                                                  \
   if (PD_ROW_TAB_##e >= 0 && use_table && y[from] < (pd_count)a.code_table_n) {      \
     const double code = a.code_table[(PD_ROW_TAB_##e < 0 ? 0 : PD_ROW_TAB_##e) *     \
                                      a.code_table_n + (int)y[from]];                 \
     if (code != 0.0) PD_TAU_APPEND(e, code)       /* never NaN: the table's dt is > 0 */ \
+  } else if (PD_ROW_TAB2_##e >= 0 && use_table2 &&                                   \
+             y[from] < (pd_count)a.code_table2_na &&                                 \
+             y[PD_ROW_TAB2B_##e < 0 ? 0 : PD_ROW_TAB2B_##e] < (pd_count)a.code_table2_nb) { \
+    const double code = a.code_table2[PD_TAU_PAIR_INDEX(e, from)];                   \
+    if (code != 0.0) PD_TAU_APPEND(e, code)                                          \
   } else PD_TAU_COMPUTED(e, rate)
 #define PD_TAU_ENTRY(e, to, is_int, rate)                                            \
   if (PD_ROW_UNI_##e >= 0 && use_table) {                                            \
@@ -265,16 +302,22 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
   } else { const double mean = rate * dt; PD_TAU_CODE(e, mean) }
 #define PD_TAU_TRANSFER(e, from, to, rate) PD_TAU_FIXED(e, from, rate)
 #define PD_TAU_DEATH(e, from, rate) PD_TAU_FIXED(e, from, rate)
-#if PD_TAU_ONE_TABLE_TEST && PD_NTAB > 0
+#if PD_TAU_ONE_TABLE_TEST && (PD_NTAB > 0 || PD_NTAB2 > 0)
       /* One test per step instead of one per row: when the launch has a table for this dt and
        * the largest count a table row looks up is inside it, every such row is a plain lookup
        * (PD_TAU_LOOKUP*); any other step takes the general rows, which test and fall back to
        * computing the code row by row. */
       bool all_in_table = false;
-      if (use_table) {
-        pd_count top = 0;
+      if ((PD_NTAB == 0 || use_table) && (PD_NTAB2 == 0 || use_table2)) {
+        pd_count top = 0, top_a = 0, top_b = 0;
 #define PD_TAU_TOP_ENTRY(e, to, is_int, rate)
-#define PD_TAU_TOP_FIXED(e, from) if (PD_ROW_TAB_##e >= 0) top = top > y[from] ? top : y[from];
+#define PD_TAU_TOP_FIXED(e, from)                                                    \
+  if (PD_ROW_TAB_##e >= 0) top = top > y[from] ? top : y[from];                      \
+  else if (PD_ROW_TAB2_##e >= 0) {                                                   \
+    top_a = top_a > y[from] ? top_a : y[from];                                       \
+    top_b = top_b > y[PD_ROW_TAB2B_##e < 0 ? 0 : PD_ROW_TAB2B_##e]                   \
+                ? top_b : y[PD_ROW_TAB2B_##e < 0 ? 0 : PD_ROW_TAB2B_##e];            \
+  }
 #define PD_TAU_TOP_TRANSFER(e, from, to, rate) PD_TAU_TOP_FIXED(e, from)
 #define PD_TAU_TOP_DEATH(e, from, rate) PD_TAU_TOP_FIXED(e, from)
         PD_FOR_EACH_LIVE_ROW(PD_TAU_TOP_ENTRY, PD_TAU_TOP_TRANSFER, PD_TAU_TOP_DEATH)
@@ -282,7 +325,10 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #undef PD_TAU_TOP_FIXED
 #undef PD_TAU_TOP_TRANSFER
 #undef PD_TAU_TOP_DEATH
-        all_in_table = top < (pd_count)a.code_table_n;       /* counts are never negative */
+        /* counts are never negative */
+        all_in_table = (PD_NTAB == 0 || top < (pd_count)a.code_table_n) &&
+                       (PD_NTAB2 == 0 || (top_a < (pd_count)a.code_table2_na &&
+                                          top_b < (pd_count)a.code_table2_nb));
       }
       if (all_in_table) {
 #define PD_TAU_LOOKUP_FIXED(e, from, rate)                                           \
@@ -290,9 +336,12 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
     const double code = a.code_table[(PD_ROW_TAB_##e < 0 ? 0 : PD_ROW_TAB_##e) *     \
                                      a.code_table_n + (int)y[from]];                 \
     if (code != 0.0) PD_TAU_APPEND(e, code)                                          \
+  } else if (PD_ROW_TAB2_##e >= 0) {                                                 \
+    const double code = a.code_table2[PD_TAU_PAIR_INDEX(e, from)];                   \
+    if (code != 0.0) PD_TAU_APPEND(e, code)                                          \
   } else PD_TAU_COMPUTED(e, rate)
 #define PD_TAU_LOOKUP_ENTRY(e, to, is_int, rate)                                     \
-  if (PD_ROW_UNI_##e >= 0) {                                                         \
+  if (PD_ROW_UNI_##e >= 0 && use_table) {                                                         \
     const double code = a.code_table[PD_NTAB * a.code_table_n +                      \
                                      (PD_ROW_UNI_##e < 0 ? 0 : PD_ROW_UNI_##e)];     \
     if (code != 0.0) {                                                               \
@@ -317,6 +366,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #undef PD_TAU_TRANSFER
 #undef PD_TAU_DEATH
 #undef PD_TAU_FIXED
+#undef PD_TAU_PAIR_INDEX
 #undef PD_TAU_COMPUTED
 #undef PD_TAU_CODE
 #undef PD_TAU_APPEND

@@ -330,6 +330,24 @@ def test_tau_leap_on_an_irregular_grid_with_repeated_and_decreasing_times():
     finally:
         del os.environ['POPDYN_CODE_TABLE']
     assert np.array_equal(with_tables, without)
+    # the pair tables of the two force-of-infection rows (count x count x beta): switched off,
+    # and so small that members leave them and come back (the rows then compute their codes):
+    # the same trajectories, and the oracle's
+    m.make_times(0, 300, 1)
+    om = oracle.OracleModel(helpers.compiled(m, 'discrete_time_stochastic'))
+    want = om.stochastic_batch('discrete_time_stochastic', n, m.get_init_list(), m.target_times,
+                               seed)
+    assert want['err'] == 0
+    finals = []
+    for setting in (None, '0,0', '1100,6', '8,4'):
+        if setting is not None:
+            os.environ['POPDYN_CODE_TABLE2'] = setting
+        try:
+            finals.append(m.integrate_ensemble('discrete_time_stochastic', n_members=n,
+                                               output='final', seed=seed).final)
+        finally:
+            os.environ.pop('POPDYN_CODE_TABLE2', None)
+        assert np.array_equal(finals[-1].T, want['soln'][:, -1, :]), setting
 
 
 def test_shard_invariance_by_global_member_id():
