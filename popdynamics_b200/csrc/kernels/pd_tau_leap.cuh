@@ -52,8 +52,15 @@ typedef pd_u64 pd_mask;
 
 /* the kernel's dynamic shared memory (the draw list), read by the host after loading the module
  * (csrc/popdyn_capi.cu) */
+/* PD_TAU_SENTINEL: the list ends with a cell holding 0.0 -- no code is ever 0.0, a row that
+ * draws nothing is not in the list -- so the draw loop learns that a lane is done from the code it
+ * has just loaded: a finished event is a store, an add, a load and three moves, with no compare
+ * of the cursor against the end of the list and nothing predicated on it. */
+#ifndef PD_TAU_SENTINEL
+#define PD_TAU_SENTINEL 1
+#endif
 extern "C" __device__ unsigned int pd_smem_bytes =
-    (unsigned int)PD_CODE_SMEM_BYTES(PD_LIVE_NROW, PD_BLOCK);
+    (unsigned int)PD_CODE_SMEM_BYTES(PD_LIVE_NROW + (PD_TAU_SENTINEL ? 1 : 0), PD_BLOCK);
 
 /* Poisson code of a mean: exp(-mean) for the multiplication method, -mean for PTRS */
 __device__ __forceinline__ double pd_tau_code(double mean) {
@@ -373,18 +380,33 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 
       /* ---- 2. draw loop.  Lane state: list cursor, the current event's code, its running
        * product and count */
+#if PD_TAU_SENTINEL
+      PD_LIST_PUT_CODE(end, 0.0);
+#endif
       pd_cursor cur = list0;
       double code = PD_LIST_CODE(list0);
       double prod = 1.0;
       int X = 0;
 /* the current event ends with draw d: park it, step to the lane's next event */
+#if PD_TAU_SENTINEL
+#define PD_TAU_MORE (__double2hiint(code) != 0)     /* codes are normal numbers or below -10 */
+#define PD_TAU_MORE_MULT (code > 0.0)               /* ... and not a PTRS event either */
+#define PD_TAU_NEXT(d)                                                               \
+  {                                                                                  \
+    PD_LIST_PARK(cur, d);                                                            \
+    cur += PD_CURSOR_STEP;                                                           \
+    code = PD_LIST_CODE(cur); prod = 1.0; X = 0;                                     \
+  }
+#else
 #define PD_TAU_MORE (cur != end)
+#define PD_TAU_MORE_MULT (cur != end && code >= 0.0)
 #define PD_TAU_NEXT(d)                                                               \
   {                                                                                  \
     PD_LIST_PARK(cur, d);                                                            \
     cur += PD_CURSOR_STEP;                                                           \
     if (cur != end) { code = PD_LIST_CODE(cur); prod = 1.0; X = 0; }                 \
   }
+#endif
 /* one uniform of the multiplication method */
 #define PD_TAU_MULT(u)                                                               \
   {                                                                                  \
@@ -422,7 +444,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
           rng.has_spare = 1;
           PD_TAU_MULT(u0)
         }
-        if (PD_TAU_MORE && code >= 0.0) {   /* the block's second uniform, or the pending spare */
+        if (PD_TAU_MORE_MULT) {             /* the block's second uniform, or the pending spare */
           rng.has_spare = 0;
           PD_TAU_MULT(rng.spare)
         }
@@ -435,6 +457,7 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #undef PD_TAU_MULT
 #undef PD_TAU_NEXT
 #undef PD_TAU_MORE
+#undef PD_TAU_MORE_MULT
 
       /* ---- 3. apply pass, flow-table order: clamp to the CURRENT source count (:833-834,
        * :839-840), move; births unclamped (:842-844).  Branch-free: a row that is not in the
