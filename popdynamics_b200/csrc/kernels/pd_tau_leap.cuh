@@ -57,7 +57,7 @@ typedef pd_u64 pd_mask;
  * has just loaded: a finished event is a store, an add, a load and three moves, with no compare
  * of the cursor against the end of the list and nothing predicated on it. */
 #ifndef PD_TAU_SENTINEL
-#define PD_TAU_SENTINEL 1
+#define PD_TAU_SENTINEL 3
 #endif
 extern "C" __device__ unsigned int pd_smem_bytes =
     (unsigned int)PD_CODE_SMEM_BYTES(PD_LIVE_NROW + (PD_TAU_SENTINEL ? 1 : 0), PD_BLOCK);
@@ -391,11 +391,19 @@ pd_tau_leap_kernel(const __grid_constant__ PdTauLaunch L) {
 #if PD_TAU_SENTINEL
 #define PD_TAU_MORE (__double2hiint(code) != 0)     /* codes are normal numbers or below -10 */
 #define PD_TAU_MORE_MULT (code > 0.0)               /* ... and not a PTRS event either */
+/* the running product restarts at 1.0 as ONE fp64 instruction, code * 0 + 1 (codes are finite
+ * wherever the product is used: a multiplication event's code is exp(-mean) in (0, 1], the
+ * sentinel is 0): the FP64 pipe is idle here, the two moves of a 64-bit constant are not free */
+#if PD_TAU_SENTINEL & 2
+#define PD_TAU_ONE(code_) __fma_rn((code_), 0.0, 1.0)
+#else
+#define PD_TAU_ONE(code_) 1.0
+#endif
 #define PD_TAU_NEXT(d)                                                               \
   {                                                                                  \
     PD_LIST_PARK(cur, d);                                                            \
     cur += PD_CURSOR_STEP;                                                           \
-    code = PD_LIST_CODE(cur); prod = 1.0; X = 0;                                     \
+    code = PD_LIST_CODE(cur); prod = PD_TAU_ONE(code); X = 0;                        \
   }
 #else
 #define PD_TAU_MORE (cur != end)
