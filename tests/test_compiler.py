@@ -281,3 +281,39 @@ def test_both_forms_of_the_compensated_sum_equal_cpython_sum():
             got = emitted(xs, form)
             assert (want == got and math.copysign(1, want) == math.copysign(1, got)) or \
                 (want != want and got != got), (form, xs, want, got)
+
+
+def test_code_table_rows_are_recognised_in_the_generated_header():
+    """The tau-leap kernel looks up the Poisson codes of two kinds of rows instead of computing
+    them: count * uniform parameter (PD_ROW_TAB_<row>: one table per parameter slot) and
+    count * (count' * uniform parameter) -- a force of infection -- (PD_ROW_TAB2_<row>: one pair
+    table per (compartment, parameter) inside the rate, PD_ROW_TAB2B_<row> that compartment).
+    A swept (per-member) parameter makes the code member dependent: no table for such a row."""
+    import re
+
+    def defines(model, method='discrete_time_stochastic'):
+        src = helpers.compiled(model, method).cuda_source()
+        return {k: v for k, v in re.findall(r'#define (PD_\w+) (.+)', src)}
+
+    d = defines(helpers.make_model('strains'))
+    labels = helpers.compiled(helpers.make_model('strains'), 'discrete_time_stochastic').labels
+    assert d['PD_NTAB2'] == '2' and d['PD_LIVE_NROW'] == '10'
+    pair_rows = [r for r in range(10) if d['PD_ROW_TAB2_%d' % r] != '-1']
+    assert pair_rows == [1, 2]                       # the two infection rows of the flow table
+    inside = {labels[int(d['PD_ROW_TAB2B_%d' % r])] for r in pair_rows}
+    assert inside == {'infectious_invader', 'infectious_resident'}
+    for r in pair_rows:
+        assert d['PD_ROW_TAB_%d' % r] == '-1'        # never both kinds
+    count_rows = [r for r in range(10) if d['PD_ROW_TAB_%d' % r] != '-1']
+    assert count_rows == [3, 4, 5, 6, 7, 8, 9] and d['PD_ROW_UNI_0'] == '0'
+    # the SIR model's force of infection is infection_beta * infectious: one pair table
+    d = defines(helpers.make_model('sir'))
+    assert d['PD_NTAB2'] == '1'
+    # ... unless beta is swept: then neither that row nor any other gets a table keyed on it
+    swept = helpers.make_model('sir')
+    swept.set_param('infection_beta', np.linspace(0.01, 0.05, 7))
+    d = defines(swept)
+    assert d['PD_NTAB2'] == '0'
+    # the ODE methods have no integer counts to key a table on
+    d = defines(helpers.make_model('strains'), 'explicit')
+    assert d['PD_NTAB2'] == '0'
