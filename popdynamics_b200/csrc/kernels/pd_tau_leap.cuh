@@ -17,13 +17,17 @@
  * of which changes which uniform goes to which event:
  *   1. RATE PASS, all lanes in lockstep: every live event's code -- exp(-mean) for the
  *      multiplication method, -mean for PTRS -- is appended to the lane's list in shared memory
- *      [k][thread]; a bit mask remembers which flow-table rows are in the list.
+ *      [k][thread]; a bit mask remembers which flow-table rows are in the list.  Codes that
+ *      depend on one or two integer counts only (count * parameter; count * count' * parameter,
+ *      a force of infection) come from tables built once per launch; one range test per step
+ *      decides whether every such row is a plain lookup.  A cell holding 0.0 closes the list.
  *   2. DRAW LOOP, flattened: the lane walks its OWN list while the warp walks the uniform stream
  *      together.  One trip = one Philox block = two uniforms for every lane; each uniform either
  *      continues the lane's current product or ends its event, whose draw X then overwrites the
- *      code in the list.  The trip count of a warp is the largest TOTAL number of uniforms any
- *      lane needs in the step, instead of the sum over events of the per-event maxima that the
- *      nested event-major loop pays.
+ *      code in the list; the lane is done when the code it loads next is the closing 0.0.  The
+ *      trip count of a warp is the largest TOTAL number of uniforms any lane needs in the step,
+ *      instead of the sum over events of the per-event maxima that the nested event-major loop
+ *      pays.
  *   3. APPLY PASS, lockstep again: the flow-table rows in order, compartment indices literal,
  *      clamp to the current source count and move.
  */
